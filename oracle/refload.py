@@ -1,0 +1,133 @@
+"""ORACLE (test infrastructure only) -- stub loader for the UNMODIFIED reference under /root/reference.
+
+Only usable in the build container (``/root/reference`` does not exist on the GPU box).  It registers a
+fake top-level ``paos`` package whose ``__path__`` points into the reference tree (so ``paos/__init__.py``,
+which needs installed metadata and matplotlib, is skipped) and stubs the third-party modules that are
+absent from this image:
+
+* ``astropy.units``        -> tiny unit objects (only ``u.m``, ``u.Unit(str)`` and ``.to()`` are used:
+                              ``paos/classes/wfo.py:882``, ``paos/classes/psd.py:148``, ``paos/core/parseConfig.py:275``)
+* ``photutils.aperture``   -> ``oracle.apertures`` (restated masks; parity unpinned, see that module)
+* ``skimage.transform``    -> functions that raise (only reached when a sag map is not on the WFO grid)
+* ``matplotlib``/``pyplot``, ``paos.core.plot`` -> empty stubs
+
+Used by ``tests/golden/make_golden.py`` (fixture generation) and by the ``not gpu`` tests that pin
+``oracle/paos_np.py`` against the real reference when it is present.
+"""
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_ROOT = "/root/reference"
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "paos", "classes"))
+
+
+class _Unit:
+    _scale = {"m": 1.0, "mm": 1e-3, "um": 1e-6, "micron": 1e-6, "nm": 1e-9, "cm": 1e-2}
+
+    def __init__(self, name):
+        name = str(name).strip()
+        if name not in self._scale:
+            raise ValueError(f"unit {name!r} not known to the oracle stub")
+        self.name = name
+
+    def to(self, other):
+        return self._scale[self.name] / self._scale[other.name]
+
+    def __repr__(self):
+        return self.name
+
+    def __eq__(self, other):
+        return isinstance(other, _Unit) and other.name == self.name
+
+    def __hash__(self):
+        return hash(self.name)
+
+
+def _make_units_module():
+    u = types.ModuleType("astropy.units")
+    u.Unit = _Unit
+    for n in _Unit._scale:
+        setattr(u, n, _Unit(n))
+    return u
+
+
+def install_stubs():
+    """Install the stub modules (idempotent).  Returns the fake ``paos`` package."""
+    if "paos" in sys.modules and getattr(sys.modules["paos"], "__oracle_stub__", False):
+        return sys.modules["paos"]
+    if not reference_available():
+        raise RuntimeError("reference tree not present; refload is only usable in the build container")
+    from loguru import logger
+
+    logger.disable("paos")
+
+    pkg = types.ModuleType("paos")
+    pkg.__path__ = [os.path.join(REFERENCE_ROOT, "paos")]
+    pkg.logger = logger
+    pkg.__author__, pkg.__pkg_name__, pkg.__version__ = "ref", "PAOS", "1.2.12"
+    pkg.__oracle_stub__ = True
+    sys.modules["paos"] = pkg
+
+    if "astropy" not in sys.modules:
+        astropy = types.ModuleType("astropy")
+        units = _make_units_module()
+        astropy.units = units
+        sys.modules["astropy"] = astropy
+        sys.modules["astropy.units"] = units
+
+    from oracle import apertures
+
+    phot = types.ModuleType("photutils")
+    phot_ap = types.ModuleType("photutils.aperture")
+    phot_ap.EllipticalAperture = apertures.EllipticalAperture
+    phot_ap.RectangularAperture = apertures.RectangularAperture
+    phot.aperture = phot_ap
+    sys.modules.setdefault("photutils", phot)
+    sys.modules.setdefault("photutils.aperture", phot_ap)
+
+    def _no_skimage(*a, **k):
+        raise RuntimeError("skimage.transform is not available: put the sag map on the WFO grid")
+
+    sk = types.ModuleType("skimage")
+    skt = types.ModuleType("skimage.transform")
+    skt.rescale = _no_skimage
+    skt.resize = _no_skimage
+    sk.transform = skt
+    sys.modules.setdefault("skimage", sk)
+    sys.modules.setdefault("skimage.transform", skt)
+
+    if "matplotlib" not in sys.modules:
+        mpl = types.ModuleType("matplotlib")
+        plt = types.ModuleType("matplotlib.pyplot")
+        mpl.pyplot = plt
+        sys.modules["matplotlib"] = mpl
+        sys.modules["matplotlib.pyplot"] = plt
+
+    plot = types.ModuleType("paos.core.plot")
+    plot.do_legend = lambda *a, **k: None
+    plot.plot_pop = lambda *a, **k: None
+    plot.simple_plot = lambda *a, **k: None
+    sys.modules["paos.core.plot"] = plot
+    return pkg
+
+
+def load():
+    """Return a namespace with the unmodified reference symbols used by the hot path."""
+    install_stubs()
+    ns = types.SimpleNamespace()
+    ns.WFO = importlib.import_module("paos.classes.wfo").WFO
+    zer = importlib.import_module("paos.classes.zernike")
+    ns.Zernike, ns.PolyOrthoNorm = zer.Zernike, zer.PolyOrthoNorm
+    ns.PSD = importlib.import_module("paos.classes.psd").PSD
+    ns.ABCD = importlib.import_module("paos.classes.abcd").ABCD
+    ns.coordinate_break = importlib.import_module("paos.core.coordinateBreak").coordinate_break
+    ns.parse_config = importlib.import_module("paos.core.parseConfig").parse_config
+    ns.run = importlib.import_module("paos.core.run").run
+    ns.Material = importlib.import_module("paos.util.material").Material
+    ns.units = sys.modules["astropy.units"]
+    return ns
