@@ -1,0 +1,157 @@
+/*
+ * paos_b200.h -- C ABI of libpaos_b200.so, the B200 (sm_100a) replacement for the array arithmetic of
+ * PAOS's Fresnel-propagation hot path.
+ *
+ * The reference (arielmission-space/PAOS v1.2.12) has no FFI boundary of its own: its operator API for
+ * this path is the Python class paos.WFO (paos/classes/wfo.py) and the chain driver paos.core.run.run
+ * (paos/core/run.py).  This header is the boundary a drop-in inserts *underneath* that class: the Python
+ * host keeps the Gaussian pilot-beam scalars (wl, z, w0, zw0, zr, dx, dy, C, fratio) exactly as the
+ * reference does and calls one entry point per array operation.  Each entry point cites the reference
+ * lines whose array arithmetic it replaces.
+ *
+ * Conventions
+ *  - plain C types only; every function returns 0 on success and a negative code on error, with a
+ *    human readable message available from paos_last_error() (thread local);
+ *  - a wavefront handle owns (or borrows) one N x N complex array, row-major [y][x], resident in HBM for
+ *    the whole surface chain; dtype PAOS_C128 matches numpy complex128, PAOS_C64 is the stated
+ *    single-precision mode;
+ *  - operations are *recorded* and executed lazily: the library fuses the elementwise factors (fftshift
+ *    signs, Fresnel chirps, lens phase, aperture masks, phase screens, the stop normalisation) into the
+ *    first/last stage of the FFT passes when the queue is flushed by a read, an explicit
+ *    paos_wfo_flush, or paos_wfo_sync.  No call except *_read, *_sync and paos_wfo_stats blocks the host;
+ *  - all device work is enqueued on the handle's CUDA stream;
+ *  - there is no CPU fallback: every entry point fails with PAOS_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef PAOS_B200_H
+#define PAOS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAOS_ABI_VERSION 1
+
+enum {
+    PAOS_OK = 0,
+    PAOS_ERR_ARG = -1,     /* bad argument (grid not 2^n in 64..4096, null pointer, ...) */
+    PAOS_ERR_CUDA = -2,    /* CUDA runtime error or no usable device */
+    PAOS_ERR_STATE = -3,   /* operation not valid in the current state */
+    PAOS_ERR_UNSUPPORTED = -4
+};
+
+enum { PAOS_C128 = 0, PAOS_C64 = 1 };
+
+/* what paos_wfo_read materialises */
+enum {
+    PAOS_READ_WFO = 0,       /* complex field (wfo.py:163-164)          -> 2*N*N reals       */
+    PAOS_READ_AMPLITUDE = 1, /* |wfo|, numpy abs (wfo.py:167-168)       -> N*N reals         */
+    PAOS_READ_PHASE = 2,     /* angle(wfo) (wfo.py:171-172)             -> N*N reals         */
+    PAOS_READ_PSF = 3        /* |wfo|^2 (paos/core/plot.py:125-130)     -> N*N reals         */
+};
+
+enum { PAOS_SHAPE_ELLIPSE = 0, PAOS_SHAPE_RECT = 1 };
+
+typedef struct paos_wfo paos_wfo; /* opaque */
+
+/* ---- library ------------------------------------------------------------------------------- */
+int paos_abi_version(void);
+const char *paos_last_error(void);
+/* number of usable sm_100 devices (0 when none); never fails */
+int paos_device_count(void);
+
+/* ---- lifetime (wfo.py:99-120: _wfo = ones((N, N), complex128)) ------------------------------ */
+/* n: grid size, power of two in [64, 4096].  device: CUDA ordinal.  stream: a cudaStream_t cast to
+ * void* (NULL = the library creates a non-blocking stream for the handle).  borrowed: optional device
+ * pointer to n*n complex elements owned by the caller (e.g. a torch CUDA tensor); NULL = the library
+ * allocates.  The field starts as all ones and is not materialised until first needed. */
+int paos_wfo_create(paos_wfo **out, int n, int dtype, int device, void *stream, void *borrowed);
+int paos_wfo_destroy(paos_wfo *w);
+/* reset to the initial all-ones field (re-use of a handle for the next chain) */
+int paos_wfo_reset(paos_wfo *w);
+/* run everything recorded so far (asynchronous) */
+int paos_wfo_flush(paos_wfo *w);
+/* flush and wait for the stream */
+int paos_wfo_sync(paos_wfo *w);
+
+/* ---- data movement --------------------------------------------------------------------------- */
+/* replace the field by host data (n*n complex, dtype of the handle); discards recorded operations */
+int paos_wfo_upload(paos_wfo *w, const void *host_src);
+/* flush, compute `what` on the device and copy it to host memory (blocking).  dst holds doubles for
+ * PAOS_C128 handles and floats for PAOS_C64 handles. */
+int paos_wfo_read(paos_wfo *w, int what, void *host_dst);
+/* same, into device memory (asynchronous on the handle's stream) */
+int paos_wfo_read_device(paos_wfo *w, int what, void *dev_dst);
+/* replace the field by n*n complex elements already in device memory (asynchronous; a no-op copy when
+ * dev_src is the handle's own buffer, i.e. the caller wrote into the borrowed tensor) */
+int paos_wfo_upload_device(paos_wfo *w, const void *dev_src);
+
+/* ---- elementwise operators ------------------------------------------------------------------- */
+/* wfo.py:203-278 (aperture): multiply by the mask (or 1-mask when obscuration != 0).  All lengths in
+ * pixels as the reference passes them to photutils: centre (ixc, iyc) = (xc/dx + N/2, yc/dy + N/2);
+ * ellipse: semi-axes (ihx, ihy), exact pixel/ellipse overlap; rectangle: full sides (ihx, ihy), 32x32
+ * sub-pixel sampling.  theta in radians; only theta == 0 is implemented (run.py:114-121 never tilts). */
+int paos_wfo_aperture(paos_wfo *w, int shape, double ixc, double iyc, double ihx, double ihy,
+                      double theta, int obscuration);
+/* wfo.py:195-201 (make_stop): divide by sqrt(sum |wfo|^2) */
+int paos_wfo_make_stop(paos_wfo *w);
+/* wfo.py:359-366 (lens): multiply by exp(i * c1*c2 * (x^2 + y^2)), x = (j - N/2)*dx, y = (i - N/2)*dy.
+ * The product c1*c2 is formed in double-double so the host can pass the reference's two rounded
+ * factors (c1 = -2*pi, c2 = 0.5*lens_phase/wl) unchanged. */
+int paos_wfo_quadphase(paos_wfo *w, double c1, double c2, double dx, double dy);
+/* wfo.py:650-652, :867-869, :947: multiply by exp(2*pi*i * screen / wl); screen = n*n host doubles
+ * (metres, 0 where masked).  The library copies it to the device. */
+int paos_wfo_phase_screen(paos_wfo *w, const double *host_screen, double wl);
+/* same with a device pointer that must stay valid until the next flush */
+int paos_wfo_phase_screen_device(paos_wfo *w, const double *dev_screen, double wl);
+/* wfo.py:574-654 + zernike.py:63-109,:210-247: wfe = sum_k coef[k] * Z_k(rho, phi) inside rho <= 1
+ * (0 outside), then multiply by exp(2*pi*i*wfe/wl).  m[k], n[k]: azimuthal / radial numbers from
+ * Zernike.j2mn; coef[k] = Z[k]*norm[k] (host applies the normalisation).  origin: 0 = 'x'
+ * (phi = atan2(y, x) + offset), 1 = 'y' (phi = atan2(x, y) + offset); offset in radians.
+ * wfe_host_out: optional n*n doubles receiving the screen (blocking when non-NULL). */
+int paos_wfo_zernike(paos_wfo *w, int nterms, const int *m, const int *n, const double *coef,
+                     double radius, double dx, double dy, double offset, int origin, double wl,
+                     double *wfe_host_out);
+/* wfo.py:873-949 + psd.py:113-148: surface-error screen with power spectrum A/(B+(f/fknee)^C) between
+ * fmin and fmax plus white roughness SR, times 2*unit_scale, applied as a phase screen.
+ * noise1/noise2: n*n host doubles replacing the reference's two np.random.randn draws (bit-parity
+ * mode); when both are NULL the library draws them on the device from `seed` (Philox + Box-Muller,
+ * statistical parity only).  wfe_host_out optional as above. */
+int paos_wfo_psd(paos_wfo *w, double A, double B, double C, double fknee, double fmin, double fmax,
+                 double SR, double unit_scale, double dx, double dy, double wl, const double *noise1,
+                 const double *noise2, uint64_t seed, double *wfe_host_out);
+
+/* ---- propagators ------------------------------------------------------------------------------ */
+/* wfo.py:462-472 (ptp): ifftshift, fft2(ortho), * exp(-i*pi*wl*dz*(fx^2+fy^2)), ifft2(ortho), fftshift */
+int paos_wfo_ptp(paos_wfo *w, double wl, double dz, double dx, double dy);
+/* wfo.py:493-509 (stw): ifftshift, fft2|ifft2 by sign of dz, * exp(+i*pi*wl*dz*(fx^2+fy^2)), fftshift */
+int paos_wfo_stw(paos_wfo *w, double wl, double dz, double dx, double dy);
+/* wfo.py:530-545 (wts): * exp(+i*pi/(dz*wl)*(x^2+y^2)), ifftshift, fft2|ifft2 by sign of dz, fftshift */
+int paos_wfo_wts(paos_wfo *w, double wl, double dz, double dx, double dy);
+/* plain shifted transform: fftshift(fft2|ifft2(ifftshift(wfo), norm="ortho")); used by tests */
+int paos_wfo_fft2(paos_wfo *w, int inverse);
+
+/* ---- statistics -------------------------------------------------------------------------------- */
+typedef struct paos_stats {
+    uint64_t kernel_launches;   /* kernels of this library launched on the handle so far */
+    uint64_t pass_launches;     /* of which FFT line-pass kernels */
+    uint64_t fft2_recorded;     /* FFT2s requested through the API (algorithmic count) */
+    uint64_t line_ffts_run;     /* 1-D line-FFT batches executed (2 per FFT2) */
+    double last_flush_ms;       /* device time of the most recent flushed batch (CUDA events), 0 if untimed */
+} paos_stats;
+int paos_wfo_stats(paos_wfo *w, paos_stats *out);
+/* enable CUDA-event timing of every pass kernel (adds two event records per launch); the per-kernel
+ * totals are reported by paos_wfo_timing */
+int paos_wfo_enable_timing(paos_wfo *w, int enable);
+/* sum of pass-kernel device times (ms) and number of timed launches since the last call */
+int paos_wfo_timing(paos_wfo *w, double *pass_ms, uint64_t *pass_launches);
+/* the same split by pass kind: col = 0 row pass / 1 column pass, nfft = line FFTs chained in the pass
+ * (0..8); reset != 0 clears the bucket after reading it */
+int paos_wfo_timing_detail(paos_wfo *w, int col, int nfft, double *ms, uint64_t *launches, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAOS_B200_H */

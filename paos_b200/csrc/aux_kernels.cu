@@ -1,0 +1,298 @@
+// aux_kernels.cu -- the small kernels around the line passes: separable phase tables, the stop
+// reduction, read-out (|.|, angle, |.|^2), the Zernike screen, PSD helpers.
+#include "aux_kernels.h"
+#include "pass_kernel.cuh"
+
+namespace paosb {
+
+// ---- separable phase tables ------------------------------------------------------------------------
+// exp(i * c1*c2 * u^2) with the phase formed in double-double and reduced mod 2*pi before sincos, so a
+// table entry is accurate to ~1 ulp even when the phase is 1e7 rad.  u is rounded exactly as numpy does:
+// x = (k - n//2) * dx   (wfo.py:359-360, :530-531)   fx = k' * (1.0/(n*d))   (numpy fftfreq, wfo.py:464-465)
+__device__ __forceinline__ void phase_term(const TableTerm& tm, int k, int n, double& cs, double& sn) {
+    const double kk = (double)(k - n / 2);
+    double u;
+    if (tm.kind == TERM_QFREQ) {
+        const double val = 1.0 / ((double)n * tm.d);
+        u = kk * val;
+    } else {
+        u = kk * tm.d;
+    }
+    const double u2 = u * u;  // rounded square, as numpy's xx**2
+    // c = c1*c2 in double-double
+    const double ch = tm.c1 * tm.c2;
+    const double cl = fma(tm.c1, tm.c2, -ch);
+    // p = c*u2 in double-double
+    const double ph = ch * u2;
+    const double pl = fma(ch, u2, -ph) + cl * u2;
+    // reduce mod 2*pi (three-term constant)
+    const double TWO_PI_H = 6.283185307179586232e+00;
+    const double TWO_PI_M = 2.449293598294706414e-16;
+    const double TWO_PI_L = -5.989539619436679332e-33;
+    const double q = rint(ph * 0.15915494309189534561);
+    double r = fma(-q, TWO_PI_H, ph);          // exact (cancellation)
+    double rl = fma(-q, TWO_PI_M, pl);
+    rl = fma(-q, TWO_PI_L, rl);
+    const double rs = r + rl;
+    const double re = rl - (rs - r);           // residual of the sum
+    double s, c;
+    sincos(rs, &s, &c);
+    cs = fma(-s, re, c);
+    sn = fma(c, re, s);
+}
+
+template <typename R>
+__global__ void build_tables_kernel(const __grid_constant__ TableBlock B) {
+    const TableSpec& sp = B.spec[blockIdx.y];
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = B.n;
+    if (k >= n) return;
+    if (sp.kind == TABLE_COUNT) {
+        // number of the 32 sub-pixel centres of pixel k strictly inside (-full/2, full/2) around the centre;
+        // accumulation order of the published photutils routine (x = x0 - d/2; x += d)
+        const double half = sp.cnt_full / 2.0;
+        const double x0 = ((double)k - 0.5) - sp.cnt_c;
+        const double x1 = x0 + 1.0;
+        const double d = (x1 - x0) / 32.0;
+        double x = x0 - 0.5 * d;
+        int cnt = 0;
+        for (int s = 0; s < 32; ++s) {
+            x += d;
+            if (fabs(x) < half) ++cnt;
+        }
+        reinterpret_cast<double*>(sp.out)[k] = (double)cnt;
+        return;
+    }
+    double re = 1.0, im = 0.0;
+    for (int i = 0; i < sp.nterms; ++i) {
+        double c, s;
+        phase_term(sp.terms[i], k, n, c, s);
+        const double nr = re * c - im * s, ni = re * s + im * c;
+        re = nr;
+        im = ni;
+    }
+    double sc = sp.scale;
+    if (sp.sign && (k & 1)) sc = -sc;
+    re *= sc;
+    im *= sc;
+    stc(reinterpret_cast<C<R>*>(sp.out) + k, C<R>((R)re, (R)im));
+}
+
+cudaError_t launch_build_tables(const TableBlock& B, cudaStream_t st) {
+    dim3 grid((B.n + 127) / 128, B.ntab);
+    if (B.dtype == 0) build_tables_kernel<double><<<grid, 128, 0, st>>>(B);
+    else build_tables_kernel<float><<<grid, 128, 0, st>>>(B);
+    return cudaGetLastError();
+}
+
+// ---- stop: sum |field * pending real factors|^2 (wfo.py:200) ----------------------------------------
+struct Norm2Params {
+    const void* src;
+    int n;
+    int ngen;
+    GenOp gen[GMAX];
+};
+
+template <typename R>
+__global__ void __launch_bounds__(256) norm2_partial_kernel(const __grid_constant__ Norm2Params P, double* __restrict__ partials) {
+    const int n = P.n;
+    const size_t total = (size_t)n * n;
+    const C<R>* src = reinterpret_cast<const C<R>*>(P.src);
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int iy = (int)(i / n), ix = (int)(i % n);
+        C<R> v = src ? ldc(src + i) : C<R>((R)1, (R)0);
+        for (int g = 0; g < P.ngen; ++g) apply_gen(v, P.gen[g], ix, iy, n);
+        acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = red[0];
+}
+
+__global__ void norm2_final_kernel(const double* __restrict__ partials, int np, double* __restrict__ out) {
+    __shared__ double red[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < np; i += 256) acc += partials[i];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[0] = 1.0 / sqrt(red[0]);
+        out[1] = red[0];
+    }
+}
+
+cudaError_t launch_norm2(const void* src, int n, int dtype, const GenOp* gen, int ngen, double* partials,
+                         int npartials, double* out_slot, cudaStream_t st) {
+    Norm2Params P;
+    P.src = src;
+    P.n = n;
+    P.ngen = ngen;
+    for (int i = 0; i < ngen; ++i) {
+        P.gen[i] = gen[i];
+    }
+    if (dtype == 0) norm2_partial_kernel<double><<<npartials, 256, 0, st>>>(P, partials);
+    else norm2_partial_kernel<float><<<npartials, 256, 0, st>>>(P, partials);
+    norm2_final_kernel<<<1, 256, 0, st>>>(partials, npartials, out_slot);
+    return cudaGetLastError();
+}
+
+// ---- read-out (wfo.py:163-172, plot.py:125-130) ------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256) readout_kernel(const C<R>* __restrict__ src, size_t total, int what, R* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const C<R> v = ldc(src + i);
+        out[i] = readout_value<R>(v, what);
+    }
+}
+
+cudaError_t launch_readout(const void* src, int n, int dtype, int what, void* out, cudaStream_t st) {
+    const size_t total = (size_t)n * n;
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    if (dtype == 0) readout_kernel<double><<<blocks, 256, 0, st>>>(reinterpret_cast<const C<double>*>(src), total, what, reinterpret_cast<double*>(out));
+    else readout_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const C<float>*>(src), total, what, reinterpret_cast<float*>(out));
+    return cudaGetLastError();
+}
+
+// ---- Zernike wavefront-error screen (wfo.py:620-647, zernike.py:77-109, :245-247) --------------------
+// Radial part through the Jacobi recurrence that scipy.special.eval_jacobi uses for integer order;
+// the binomial prefactor and (-1)^k are folded into coef[] by the host.
+__device__ __forceinline__ double jacobi_m0(int k, int m, double x) {
+    // P_k^{(m,0)}(x) / binom(k+m, k)
+    if (k == 0) return 1.0;
+    const double alpha = (double)m;
+    double d = (alpha + 2.0) * (x - 1.0) / (2.0 * (alpha + 1.0));
+    double p = d + 1.0;
+    for (int kk = 0; kk < k - 1; ++kk) {
+        const double kf = kk + 1.0;
+        const double t = 2.0 * kf + alpha;
+        d = ((t * (t + 1.0) * (t + 2.0)) * (x - 1.0) * p + 2.0 * kf * kf * (t + 2.0) * d) /
+            (2.0 * (kf + alpha + 1.0) * (kf + alpha + 1.0) * t);
+        p = d + p;
+    }
+    return p;
+}
+
+__global__ void __launch_bounds__(256) zernike_kernel(const __grid_constant__ ZernParams Z, double* __restrict__ out) {
+    const int n = Z.n;
+    const size_t total = (size_t)n * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int iy = (int)(i / n), ix = (int)(i % n);
+        const double x = (double)(ix - n / 2) * Z.dx, y = (double)(iy - n / 2) * Z.dy;
+        const double r = sqrt(x * x + y * y);
+        const double rho = r / Z.radius;
+        double wfe = 0.0;
+        if (rho <= 1.0) {
+            // unit vector of the polar angle (origin x: atan2(y, x); origin y: atan2(x, y)), rotated by the offset
+            double c0, s0;
+            if (r > 0.0) {
+                c0 = (Z.origin == 0 ? x : y) / r;
+                s0 = (Z.origin == 0 ? y : x) / r;
+            } else {
+                c0 = 1.0;
+                s0 = 0.0;
+            }
+            const double c1 = c0 * Z.cos_off - s0 * Z.sin_off, s1 = s0 * Z.cos_off + c0 * Z.sin_off;
+            const double xj = 1.0 - 2.0 * (rho * rho);
+            for (int k = 0; k < Z.K; ++k) {
+                const int m = Z.m[k], am = m < 0 ? -m : m, kr = (Z.nn[k] - am) / 2;
+                // rho^|m| and cos/sin(|m| phi) by repeated multiplication
+                double rp = 1.0, cm = 1.0, sm = 0.0;
+                for (int q = 0; q < am; ++q) {
+                    rp *= rho;
+                    const double nc = cm * c1 - sm * s1;
+                    sm = sm * c1 + cm * s1;
+                    cm = nc;
+                }
+                const double ang = (m > 0) ? cm : ((m < 0) ? sm : 1.0);
+                wfe += Z.coef[k] * (rp * jacobi_m0(kr, am, xj)) * ang;
+            }
+        }
+        if (Z.accumulate) out[i] += wfe;
+        else out[i] = wfe;
+    }
+}
+
+cudaError_t launch_zernike(const ZernParams& Z, double* out, cudaStream_t st) {
+    const size_t total = (size_t)Z.n * Z.n;
+    const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    zernike_kernel<<<blocks, 256, 0, st>>>(Z, out);
+    return cudaGetLastError();
+}
+
+// ---- PSD helpers (psd.py:113-148) --------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256) real_to_complex_kernel(const double* __restrict__ src, size_t total, C<R>* __restrict__ dst) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        stc(dst + i, C<R>((R)src[i], (R)0));
+}
+template <typename R>
+__global__ void __launch_bounds__(256) psd_finalize_kernel(const C<R>* __restrict__ f, const double* __restrict__ noise2, double SR,
+                                                           double unit, double inv_nn, size_t total, double* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        double w = (double)ldc(f + i).x * inv_nn;     // ifft2 default normalisation 1/(Nx*Ny)
+        if (noise2) w += SR * noise2[i];
+        w *= 2.0;
+        w *= unit;
+        out[i] = w;
+    }
+}
+
+cudaError_t launch_real_to_complex(const double* src, int n, int dtype, void* dst, cudaStream_t st) {
+    const size_t total = (size_t)n * n;
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    if (dtype == 0) real_to_complex_kernel<double><<<blocks, 256, 0, st>>>(src, total, reinterpret_cast<C<double>*>(dst));
+    else real_to_complex_kernel<float><<<blocks, 256, 0, st>>>(src, total, reinterpret_cast<C<float>*>(dst));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_psd_finalize(const void* f, int n, int dtype, const double* noise2, double SR, double unit, double* out,
+                                cudaStream_t st) {
+    const size_t total = (size_t)n * n;
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    const double inv_nn = 1.0 / ((double)n * (double)n);
+    if (dtype == 0) psd_finalize_kernel<double><<<blocks, 256, 0, st>>>(reinterpret_cast<const C<double>*>(f), noise2, SR, unit, inv_nn, total, out);
+    else psd_finalize_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const C<float>*>(f), noise2, SR, unit, inv_nn, total, out);
+    return cudaGetLastError();
+}
+
+// standard normal field: Philox-4x32-10 counter + Box-Muller (fast mode of paos_wfo_psd; statistical parity only)
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* o) {
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+__global__ void __launch_bounds__(256) normal_kernel(uint64_t seed, uint32_t stream_id, size_t total, double* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (total + 1) / 2; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t o[4];
+        philox4x32((uint32_t)i, (uint32_t)(i >> 32), stream_id, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+        const double u1 = ((double)(((uint64_t)o[0] << 21) ^ (o[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+        const double u2 = ((double)(((uint64_t)o[2] << 21) ^ (o[3] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+        const double rad = sqrt(-2.0 * log(u1));
+        double s, c;
+        sincospi(2.0 * u2, &s, &c);
+        out[2 * i] = rad * c;
+        if (2 * i + 1 < total) out[2 * i + 1] = rad * s;
+    }
+}
+cudaError_t launch_normal(uint64_t seed, uint32_t stream_id, int n, double* out, cudaStream_t st) {
+    const size_t total = (size_t)n * n;
+    const int blocks = (int)((total / 2 + 255) / 256 < 148 * 8 ? (total / 2 + 255) / 256 : 148 * 8);
+    normal_kernel<<<blocks, 256, 0, st>>>(seed, stream_id, total, out);
+    return cudaGetLastError();
+}
+
+}  // namespace paosb

@@ -1,0 +1,88 @@
+// device_types.h -- plain structs shared by the host planner and the CUDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace paosb {
+
+constexpr int KMAX = 8;   // line FFTs chained in one pass kernel
+constexpr int GMAX = 12;  // general (non-separable) factors applied by one pass kernel
+constexpr int TERM_MAX = 8;
+constexpr int TB_MAX = 64;  // tables built by one launch of the table builder (kernel parameters may be 32 KB on sm_70+)
+
+// general elementwise factors (real masks, phase screens, device scalars)
+enum GenKind : int {
+    GEN_NONE = 0,
+    GEN_ELLIPSE = 1,    // exact pixel/ellipse overlap (theta = 0): p0=xc p1=yc p2=1/a p3=1/b p4=a*b
+    GEN_RECT = 2,       // 32x32 sub-pixel rectangle: ptr0 = x counts, ptr1 = y counts (double[N])
+    GEN_SCREEN = 3,     // exp(i*(2*pi*w)/wl): ptr0 = w (double[N*N]), p0 = wl
+    GEN_SCALE_DEV = 4,  // multiply by *ptr0 (double in device memory)
+    GEN_PSD = 5         // PSD amplitude filter in frequency space (psd.py:121-129), see aux_kernels.cu
+};
+
+struct GenOp {
+    int kind;
+    int pos;   // position in the pass program: 0 = before the first FFT, k = after the k-th FFT
+    int flag;  // ellipse / rect: 1 = obscuration (use 1 - mask)
+    int pad;
+    double p0, p1, p2, p3, p4, p5, p6, p7, p8;
+    const void* ptr0;
+    const void* ptr1;
+};
+
+struct PassParams {
+    const void* src;  // null = field of ones (never materialised)
+    void* dst;
+    int nfft;
+    int ngen;
+    int dir[KMAX];             // +1 forward, -1 inverse
+    const void* tab[KMAX + 1]; // along-line complex tables (null = none), applied after gen ops of that position
+    double scl[KMAX + 1];      // real scale used when tab[k] is null (1.0 = nothing)
+    const void* ctab_in;       // cross-axis complex table, one value per line, applied at position 0 (null = none)
+    const void* ctab_out;      // same, applied after the last position
+    int readout;               // 0: store the complex field; PAOS_READ_* (1..3): store a real read-out into dst_real instead
+    int pad;
+    void* dst_real;
+    GenOp gen[GMAX];
+};
+
+// one separable phase term: exp(i * c1*c2 * u^2), u = (k - n/2) * d  (QSPACE)  or  (k - n/2) * (1/(n*d))  (QFREQ)
+enum TermKind : int { TERM_QSPACE = 1, TERM_QFREQ = 2 };
+struct TableTerm {
+    int kind;
+    int pad;
+    double c1, c2, d;
+};
+
+enum TableKind : int { TABLE_PHASE = 0, TABLE_COUNT = 1 };
+struct TableSpec {
+    void* out;
+    int kind;      // TABLE_PHASE: complex table; TABLE_COUNT: double table of sub-pixel counts
+    int nterms;
+    int sign;      // multiply by (-1)^k
+    int pad;
+    double scale;  // real scale folded in
+    double cnt_c, cnt_full;  // TABLE_COUNT: aperture centre (pixels) and full side (pixels)
+    TableTerm terms[TERM_MAX];
+};
+struct TableBlock {
+    int ntab;
+    int n;
+    int dtype;  // 0: complex128 tables, 1: complex64 tables (count tables are always double)
+    int pad;
+    TableSpec spec[TB_MAX];
+};
+
+constexpr int ZERN_MAX = 64;
+struct ZernParams {
+    int K;
+    int origin;  // 0 = 'x', 1 = 'y'
+    int n;
+    int accumulate;  // 1: add to existing out
+    double radius, dx, dy, cos_off, sin_off;
+    int m[ZERN_MAX];
+    int nn[ZERN_MAX];
+    double coef[ZERN_MAX];   // Z[k]*norm[k]*binom(k_r+|m|, k_r)*(-1)^k_r
+};
+
+}  // namespace paosb

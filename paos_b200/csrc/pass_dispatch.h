@@ -1,0 +1,12 @@
+// pass_dispatch.h -- host entry points of the pass kernels (one translation unit per precision).
+#pragma once
+#include "device_types.h"
+
+namespace paosb {
+// points per thread (= first/last radix) used for grid size n
+inline int geom_E(int n) { return (n == 64 || n == 128 || n == 512) ? 8 : 16; }
+cudaError_t launch_pass_c128(int n, bool col, const PassParams& P, const void* tw1, const void* tw2,
+                             cudaStream_t st, int device);
+cudaError_t launch_pass_c64(int n, bool col, const PassParams& P, const void* tw1, const void* tw2,
+                            cudaStream_t st, int device);
+}  // namespace paosb

@@ -1,0 +1,249 @@
+// pass_kernel.cuh -- the line-pass kernel: one kernel = one sweep of the wavefront through HBM.
+//
+// A pass loads every line (row or column) of the N x N complex field once, runs a small *program* on it
+// in registers -- diagonal factors and up to KMAX line FFTs -- and stores it once.  Because the Fresnel
+// chirps, the lens phase and the fftshift signs are separable (exp(i c (x^2+y^2)) = exp(i c x^2) *
+// exp(i c y^2)), a run of FFT2s with only separable factors between them factorises into ONE row pass
+// and ONE column pass; non-separable factors (aperture masks, phase screens, the stop scalar) are applied
+// as "general ops" between two chained line transforms.  The host planner (runtime.cu) builds the program.
+//
+// Replaces the array arithmetic of paos/classes/wfo.py:200-201 (make_stop scale), :273-276 (aperture),
+// :359-366 (lens), :462-472 (ptp), :493-509 (stw), :530-545 (wts), :650-652/:867-869/:947 (phase screens).
+#pragma once
+#include "device_types.h"
+#include "fft_core.cuh"
+
+namespace paosb {
+
+// ---- exact area of the unit disk inside an axis-aligned rectangle ----------------------------------
+// First-quadrant piece 0 <= x0 <= x1, 0 <= y0 <= y1 :  integral over x of clamp(sqrt(1-x^2), y0, y1) - y0.
+__device__ __forceinline__ double disk_rect_q1(double x0, double x1, double y0, double y1) {
+    if (x1 <= x0 || y1 <= y0) return 0.0;
+    if (x0 * x0 + y0 * y0 >= 1.0) return 0.0;
+    if (x1 * x1 + y1 * y1 <= 1.0) return (x1 - x0) * (y1 - y0);
+    const double xa = (y1 < 1.0) ? sqrt(fmax(0.0, 1.0 - y1 * y1)) : 0.0;  // arc crosses the top edge
+    const double xb = (y0 < 1.0) ? sqrt(fmax(0.0, 1.0 - y0 * y0)) : 0.0;  // arc crosses the bottom edge
+    const double L = fmin(fmax(xa, x0), x1);
+    const double U = fmin(fmax(xb, x0), x1);
+    double area = (y1 - y0) * (L - x0);
+    if (U > L) {
+        const double sL = sqrt(fmax(0.0, 1.0 - L * L));
+        const double sU = sqrt(fmax(0.0, 1.0 - U * U));
+        // area under the arc = trapezoid under the chord + circular segment
+        const double sn = U * sL - L * sU;  // sin of the angle between the two radius vectors
+        const double cs = L * U + sL * sU;
+        const double th = atan2(sn, cs);
+        double seg;
+        if (th < 0.05) {
+            const double t2 = th * th;
+            seg = th * t2 * (1.0 / 6.0) * (1.0 - t2 * (1.0 / 20.0) * (1.0 - t2 * (1.0 / 42.0) * (1.0 - t2 * (1.0 / 72.0))));
+        } else {
+            seg = th - sn;
+        }
+        area += (0.5 * (sL + sU) - y0) * (U - L) + 0.5 * seg;
+    }
+    return area;
+}
+
+static __device__ __noinline__ double disk_rect_area(double u0, double u1, double v0, double v1) {
+    // split at the axes and fold every piece into the first quadrant
+    double xa0 = fmax(u0, 0.0), xa1 = u1;            // x >= 0 part
+    double xb0 = fmax(-u1, 0.0), xb1 = -u0;          // x <= 0 part, mirrored
+    double ya0 = fmax(v0, 0.0), ya1 = v1;
+    double yb0 = fmax(-v1, 0.0), yb1 = -v0;
+    double a = 0.0;
+    if (xa1 > xa0) {
+        if (ya1 > ya0) a += disk_rect_q1(xa0, xa1, ya0, ya1);
+        if (yb1 > yb0) a += disk_rect_q1(xa0, xa1, yb0, yb1);
+    }
+    if (xb1 > xb0) {
+        if (ya1 > ya0) a += disk_rect_q1(xb0, xb1, ya0, ya1);
+        if (yb1 > yb0) a += disk_rect_q1(xb0, xb1, yb0, yb1);
+    }
+    return a;
+}
+
+// area fraction of the unit pixel centred on (ix, iy) inside the ellipse (theta = 0)
+__device__ __forceinline__ double ellipse_fraction(const GenOp& g, double ix, double iy) {
+    const double px = ix - g.p0, py = iy - g.p1;
+    const double u0 = (px - 0.5) * g.p2, u1 = (px + 0.5) * g.p2;
+    const double v0 = (py - 0.5) * g.p3, v1 = (py + 0.5) * g.p3;
+    const double uf = fmax(fabs(u0), fabs(u1)), vf = fmax(fabs(v0), fabs(v1));
+    if (uf * uf + vf * vf <= 1.0) return 1.0;
+    const double un = (u0 <= 0.0 && u1 >= 0.0) ? 0.0 : fmin(fabs(u0), fabs(u1));
+    const double vn = (v0 <= 0.0 && v1 >= 0.0) ? 0.0 : fmin(fabs(v0), fabs(v1));
+    if (un * un + vn * vn >= 1.0) return 0.0;
+    double f = disk_rect_area(u0, u1, v0, v1) * g.p4;
+    return fmin(fmax(f, 0.0), 1.0);
+}
+
+// PSD amplitude filter sqrt(psd2d)*sqrt(N*N), zero outside [fmin, fmax] (psd.py:118-129, wfo.py:913-918).
+// p0=A p1=B p2=C p3=fknee p4=fmin p5=fmax p6=valx p7=valy p8=N ; frequencies in unshifted (fftfreq) order
+static __device__ __noinline__ double psd_filter(const GenOp& g, int ix, int iy) {
+    const int n = (int)g.p8;
+    const double kx = (double)(ix < n / 2 ? ix : ix - n), ky = (double)(iy < n / 2 ? iy : iy - n);
+    const double fx = kx * g.p6, fy = ky * g.p7;
+    double f = sqrt(fx * fx + fy * fy);
+    if (f == 0.0) f = 1e-100;
+    if (f < g.p4 || f > g.p5) return 0.0;
+    const double dfx = 2.0 * g.p6 - 1.0 * g.p6, dfy = 2.0 * g.p7 - 1.0 * g.p7;  // f[0,2]-f[0,1], f[2,0]-f[1,0]
+    const double psd2d = g.p0 / (g.p1 + pow(f / g.p3, g.p2)) / (2.0 * 3.141592653589793 * f) * (dfx * dfy);
+    return sqrt(psd2d) * sqrt((double)n * (double)n);
+}
+
+// |.|, angle or |.|^2 of one element (what = PAOS_READ_AMPLITUDE / _PHASE / _PSF)
+template <typename R> __device__ __forceinline__ R readout_value(C<R> v, int what) {
+    if (what == 1) return (R)hypot((double)v.x, (double)v.y);
+    if (what == 2) return (R)atan2((double)v.y, (double)v.x);
+    return v.x * v.x + v.y * v.y;
+}
+
+// real or complex factor of a general op at pixel (ix, iy); returns false when the factor is exactly 1
+template <typename R>
+__device__ __forceinline__ void apply_gen(C<R>& v, const GenOp& g, int ix, int iy, int n) {
+    switch (g.kind) {
+        case GEN_ELLIPSE: {
+            double m = ellipse_fraction(g, (double)ix, (double)iy);
+            if (g.flag) m = 1.0 - m;
+            v = v * (R)m;
+        } break;
+        case GEN_RECT: {
+            const double cx = __ldg((const double*)g.ptr0 + ix), cy = __ldg((const double*)g.ptr1 + iy);
+            double m = (cy * cx) / 1024.0;
+            if (g.flag) m = 1.0 - m;
+            v = v * (R)m;
+        } break;
+        case GEN_SCREEN: {
+            const double w = __ldg((const double*)g.ptr0 + (size_t)iy * n + ix);
+            if (w != 0.0) {
+                double s, c;
+                sincos((6.283185307179586 * w) / g.p0, &s, &c);
+                v = v * C<R>((R)c, (R)s);
+            }
+        } break;
+        case GEN_SCALE_DEV: {
+            v = v * (R)__ldg((const double*)g.ptr0);
+        } break;
+        case GEN_PSD: {
+            v = v * (R)psd_filter(g, ix, iy);
+        } break;
+        default: break;
+    }
+}
+
+// ---- the pass kernel ---------------------------------------------------------------------------------
+// R: real type; N: line length; E: points per thread; W: lines per CTA; COL: lines are columns.
+template <typename R, int N, int E, int W, bool COL, int MINB>
+__global__ void __launch_bounds__(W*(N / E), MINB)
+    pass_kernel(const __grid_constant__ PassParams P, const C<R>* __restrict__ tw1, const C<R>* __restrict__ tw2) {
+    using G = LineGeom<N, E>;
+    constexpr int T = G::T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C<R>* smem = reinterpret_cast<C<R>*>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int w = COL ? (tid % W) : (tid / T);
+    const int t = COL ? (tid / W) : (tid % T);
+    const int line = blockIdx.x * W + w;
+    C<R>* sm = smem + w * G::line_stride(COL ? W : 1);
+    auto sync = [] { __syncthreads(); };
+
+    const C<R>* src = reinterpret_cast<const C<R>*>(P.src);
+    C<R>* dst = reinterpret_cast<C<R>*>(P.dst);
+
+    C<R> v[E];
+    if (src) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int idx = t + j * T;
+            const size_t ga = COL ? ((size_t)idx * N + line) : ((size_t)line * N + idx);
+            v[j] = ldc(src + ga);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < E; ++j) v[j] = C<R>((R)1, (R)0);
+    }
+
+    auto diag = [&](int pos) {
+        for (int g = 0; g < P.ngen; ++g) {
+            if (P.gen[g].pos != pos) continue;
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                const int idx = t + j * T;
+                apply_gen(v[j], P.gen[g], COL ? line : idx, COL ? idx : line, N);
+            }
+        }
+        const C<R>* tab = reinterpret_cast<const C<R>*>(P.tab[pos]);
+        if (tab) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) v[j] = v[j] * ldc_ro(tab + t + j * T);
+        } else {
+            const R s = (R)P.scl[pos];
+            if (s != (R)1) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) v[j] = v[j] * s;
+            }
+        }
+    };
+
+    if (P.ctab_in) {
+        const C<R> c = ldc_ro(reinterpret_cast<const C<R>*>(P.ctab_in) + line);
+#pragma unroll
+        for (int j = 0; j < E; ++j) v[j] = v[j] * c;
+    }
+    diag(0);
+    for (int k = 0; k < P.nfft; ++k) {
+        const bool inv = P.dir[k] < 0;
+        if (inv) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) v[j] = C<R>(v[j].y, v[j].x);
+        }
+        line_fft_fwd<G, R>(v, t, sm, tw1, tw2, sync);
+        if (inv) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) v[j] = C<R>(v[j].y, v[j].x);
+        }
+        diag(k + 1);
+    }
+    if (P.ctab_out) {
+        const C<R> c = ldc_ro(reinterpret_cast<const C<R>*>(P.ctab_out) + line);
+#pragma unroll
+        for (int j = 0; j < E; ++j) v[j] = v[j] * c;
+    }
+
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+        const int idx = t + j * T;
+        const size_t ga = COL ? ((size_t)idx * N + line) : ((size_t)line * N + idx);
+        stc(dst + ga, v[j]);
+    }
+    if (P.readout) {
+        // fused read-out (wfo.py:167-172, plot.py:125-130) so a snapshot costs no extra sweep
+        R* out = reinterpret_cast<R*>(P.dst_real);
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int idx = t + j * T;
+            const size_t ga = COL ? ((size_t)idx * N + line) : ((size_t)line * N + idx);
+            out[ga] = readout_value<R>(v[j], P.readout);
+        }
+    }
+}
+
+// host-side launcher table -------------------------------------------------------------------------
+template <typename R, int N, int E, int W, bool COL, int MINB>
+cudaError_t launch_pass_t(const PassParams& P, const void* tw1, const void* tw2, cudaStream_t st, int device) {
+    using G = LineGeom<N, E>;
+    constexpr int threads = W * G::T;
+    const size_t smem = (size_t)W * G::line_stride(COL ? W : 1) * sizeof(C<R>);
+    auto kern = pass_kernel<R, N, E, W, COL, MINB>;
+    static bool configured[64] = {};  // per instantiation and device
+    if (!configured[device & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[device & 63] = true;
+    }
+    kern<<<N / W, threads, smem, st>>>(P, reinterpret_cast<const C<R>*>(tw1), reinterpret_cast<const C<R>*>(tw2));
+    return cudaGetLastError();
+}
+
+}  // namespace paosb

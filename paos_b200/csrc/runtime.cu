@@ -1,0 +1,1056 @@
+// runtime.cu -- host side of libpaos_b200.so: the wavefront handle, the operation queue, the planner that
+// turns a run of recorded operations into line passes, and the C ABI of include/paos_b200.h.
+//
+// Planner in one paragraph.  Every recorded operation is either an FFT2, a *separable* diagonal factor
+// (fftshift signs, Fresnel chirps, lens phase, the ortho scales: f(x)*g(y)), or a *general* pointwise factor
+// (aperture masks, phase screens, the stop scalar).  An FFT2 is FFTx * FFTy and a separable factor is
+// Dx * Dy, and everything that acts along x commutes with everything that acts along y.  The queue is
+// therefore split into an x-thread and a y-thread of 1-D items that only have to meet at the general
+// factors ("barriers").  A row pass executes the x-thread up to a barrier the y-thread has not reached
+// yet, a column pass does the same for the y-thread, and the pass that arrives second applies the general
+// factor in registers and carries on.  A chain of K FFT2s with G general factors between them costs about
+// G + 2 sweeps of the wavefront through HBM instead of 2K (plus ~10 elementwise sweeps per primitive in
+// the reference, paos/classes/wfo.py:462-472).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/paos_b200.h"
+#include "aux_kernels.h"
+#include "device_types.h"
+#include "pass_dispatch.h"
+
+using namespace paosb;
+
+// ---------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(PAOS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// twiddle tables (one set per device, grid size and precision; shared by all handles)
+// ---------------------------------------------------------------------------------------------------
+struct Twiddles {
+    void* tw1 = nullptr;
+    void* tw2 = nullptr;
+};
+static std::mutex g_tw_mutex;
+static std::map<long, Twiddles> g_tw;
+
+static void unit_root(long k, long n, double& c, double& s) {
+    // exp(-2*pi*i*k/n) with the argument reduced to the first octant in exact integer arithmetic
+    k %= n;
+    if (k < 0) k += n;
+    const long double PI = 3.14159265358979323846264338327950288L;
+    long oct = (8 * k) / n;               // octant 0..7
+    long double cc, ss;
+    long r8 = 8 * k - oct * n;            // position inside the octant, in units of 2*pi/(8n)
+    long double a = (2.0L * PI * (long double)r8) / (8.0L * (long double)n);
+    long double b = (2.0L * PI * (long double)(n - r8)) / (8.0L * (long double)n);  // pi/4 - a
+    switch (oct) {
+        case 0: cc = cosl(a); ss = sinl(a); break;
+        case 1: cc = sinl(b); ss = cosl(b); break;
+        case 2: cc = -sinl(a); ss = cosl(a); break;
+        case 3: cc = -cosl(b); ss = sinl(b); break;
+        case 4: cc = -cosl(a); ss = -sinl(a); break;
+        case 5: cc = -sinl(b); ss = -cosl(b); break;
+        case 6: cc = sinl(a); ss = -cosl(a); break;
+        default: cc = cosl(b); ss = -sinl(b); break;
+    }
+    c = (double)cc;
+    s = (double)(-ss);
+}
+
+static int get_twiddles(int device, int n, int dtype, Twiddles& out) {
+    std::lock_guard<std::mutex> lock(g_tw_mutex);
+    const long key = ((long)device << 32) | ((long)n << 2) | dtype;
+    auto it = g_tw.find(key);
+    if (it != g_tw.end()) {
+        out = it->second;
+        return PAOS_OK;
+    }
+    const int E = geom_E(n), T = n / E, R2 = n / (E * E);
+    const size_t n1 = (size_t)(E - 1) * T, n2 = (R2 > 1) ? (size_t)(R2 - 1) * E : 1;
+    std::vector<double> h1(2 * n1), h2(2 * n2, 0.0);
+    for (int k1 = 1; k1 < E; ++k1)
+        for (int t = 0; t < T; ++t) unit_root((long)k1 * t, n, h1[2 * ((size_t)(k1 - 1) * T + t)], h1[2 * ((size_t)(k1 - 1) * T + t) + 1]);
+    if (R2 > 1)
+        for (int k2 = 1; k2 < R2; ++k2)
+            for (int n3 = 0; n3 < E; ++n3) unit_root((long)k2 * n3, T, h2[2 * ((size_t)(k2 - 1) * E + n3)], h2[2 * ((size_t)(k2 - 1) * E + n3) + 1]);
+    Twiddles tw;
+    const size_t es = dtype == PAOS_C128 ? sizeof(double) : sizeof(float);
+    CU(cudaMalloc(&tw.tw1, 2 * n1 * es));
+    CU(cudaMalloc(&tw.tw2, 2 * n2 * es));
+    if (dtype == PAOS_C128) {
+        CU(cudaMemcpy(tw.tw1, h1.data(), 2 * n1 * es, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(tw.tw2, h2.data(), 2 * n2 * es, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float> f1(h1.begin(), h1.end()), f2(h2.begin(), h2.end());
+        CU(cudaMemcpy(tw.tw1, f1.data(), 2 * n1 * es, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(tw.tw2, f2.data(), 2 * n2 * es, cudaMemcpyHostToDevice));
+    }
+    g_tw[key] = tw;
+    out = tw;
+    return PAOS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the operation queue
+// ---------------------------------------------------------------------------------------------------
+enum OpKind { OP_FFT = 1, OP_SIGN = 2, OP_PHASE = 3, OP_GEN = 4, OP_FFT_RAW = 5 };
+
+struct Op {
+    int kind;
+    int dir;            // OP_FFT / OP_FFT_RAW: +1 forward, -1 inverse
+    double raw_scale;   // OP_FFT_RAW: real scale applied with the x half
+    TableTerm tx, ty;   // OP_PHASE: the x and y halves
+    GenOp gen;          // OP_GEN
+};
+
+// items of one axis thread
+enum ItemKind { IT_TERM = 1, IT_SIGN = 2, IT_SCALE = 3, IT_FFT = 4, IT_BARRIER = 5 };
+struct Item {
+    int kind;
+    int dir;
+    int gen;  // index into the gen list for barriers
+    double scale;
+    TableTerm term;
+};
+
+struct PosAcc {  // what accumulates at one position of a pass
+    int nterms = 0;
+    bool sign = false;
+    double scale = 1.0;
+    TableTerm terms[TERM_MAX];
+    bool trivial() const { return nterms == 0 && !sign; }
+};
+
+struct TimedLaunch {
+    cudaEvent_t a, b;
+    int nfft;
+    int col;
+};
+
+struct paos_wfo {
+    int n = 0, dtype = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    void* field = nullptr;
+    bool own_field = false;
+    bool materialized = false;  // false: the field is all ones and lives nowhere yet
+    size_t elem = 16;           // bytes per complex element
+    Twiddles tw;
+    std::vector<Op> ops;
+
+    // along-line table pool (bump allocated per flush; stream order makes reuse safe)
+    char* tab_pool = nullptr;
+    size_t tab_cap = 0, tab_used = 0;
+    // N*N double buffers (phase screens, read-out staging, PSD scratch)
+    std::vector<double*> screens_free, screens_busy;
+    void* scratch_field = nullptr;  // complex scratch for the PSD screen
+    double* partials = nullptr;
+    double* slots = nullptr;  // stop scalars: pairs (1/sqrt(sum), sum)
+    int slot_next = 0;
+    static constexpr int NSLOTS = 256;
+    static constexpr int NPARTIALS = 148 * 8;
+
+    paos_stats stats{};
+    bool timing = false;
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> event_pool;
+    double timed_ms[2][KMAX + 1] = {};
+    uint64_t timed_n[2][KMAX + 1] = {};
+};
+
+static int set_device(paos_wfo* w) {
+    CU(cudaSetDevice(w->device));
+    return PAOS_OK;
+}
+
+static int alloc_table(paos_wfo* w, size_t bytes, void** out) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (w->tab_used + bytes > w->tab_cap) return fail(PAOS_ERR_STATE, "table pool exhausted");
+    *out = w->tab_pool + w->tab_used;
+    w->tab_used += bytes;
+    return PAOS_OK;
+}
+
+static int get_screen(paos_wfo* w, double** out) {
+    if (!w->screens_free.empty()) {
+        *out = w->screens_free.back();
+        w->screens_free.pop_back();
+    } else {
+        CU(cudaMalloc((void**)out, (size_t)w->n * w->n * sizeof(double)));
+    }
+    w->screens_busy.push_back(*out);
+    return PAOS_OK;
+}
+
+static void recycle_screens(paos_wfo* w) {
+    // every consumer of a busy screen has been enqueued; later writers are ordered behind them on the stream
+    for (double* p : w->screens_busy) w->screens_free.push_back(p);
+    w->screens_busy.clear();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// planner
+// ---------------------------------------------------------------------------------------------------
+static void split_ops(const paos_wfo* w, const std::vector<Op>& ops, std::vector<Item>& X, std::vector<Item>& Y,
+                      std::vector<GenOp>& gens) {
+    const double ortho = 1.0 / std::sqrt((double)w->n);
+    for (const Op& op : ops) {
+        Item ix{}, iy{};
+        switch (op.kind) {
+            case OP_FFT:
+                ix.kind = iy.kind = IT_FFT;
+                ix.dir = iy.dir = op.dir;
+                X.push_back(ix);
+                Y.push_back(iy);
+                ix.kind = iy.kind = IT_SCALE;
+                ix.scale = iy.scale = ortho;
+                X.push_back(ix);
+                Y.push_back(iy);
+                break;
+            case OP_FFT_RAW:
+                ix.kind = iy.kind = IT_FFT;
+                ix.dir = iy.dir = op.dir;
+                X.push_back(ix);
+                Y.push_back(iy);
+                if (op.raw_scale != 1.0) {
+                    ix.kind = IT_SCALE;
+                    ix.scale = op.raw_scale;
+                    X.push_back(ix);
+                }
+                break;
+            case OP_SIGN:
+                ix.kind = iy.kind = IT_SIGN;
+                X.push_back(ix);
+                Y.push_back(iy);
+                break;
+            case OP_PHASE:
+                ix.kind = iy.kind = IT_TERM;
+                ix.term = op.tx;
+                iy.term = op.ty;
+                X.push_back(ix);
+                Y.push_back(iy);
+                break;
+            case OP_GEN:
+                ix.kind = iy.kind = IT_BARRIER;
+                ix.gen = iy.gen = (int)gens.size();
+                gens.push_back(op.gen);
+                X.push_back(ix);
+                Y.push_back(iy);
+                break;
+        }
+    }
+}
+
+static bool is_diag(const Item& it) { return it.kind == IT_TERM || it.kind == IT_SIGN || it.kind == IT_SCALE; }
+
+static bool acc_item(PosAcc& a, const Item& it) {
+    if (it.kind == IT_SIGN) a.sign = !a.sign;
+    else if (it.kind == IT_SCALE) a.scale *= it.scale;
+    else {
+        if (a.nterms == TERM_MAX) return false;
+        a.terms[a.nterms++] = it.term;
+    }
+    return true;
+}
+
+struct PlannedPass {
+    bool col;
+    PassParams P;
+};
+
+struct Plan {
+    std::vector<PlannedPass> passes;
+    std::vector<TableSpec> specs;
+};
+
+static int spec_from_acc(paos_wfo* w, const PosAcc& a, Plan& plan, const void** tab_out) {
+    void* mem;
+    int rc = alloc_table(w, (size_t)w->n * w->elem, &mem);
+    if (rc) return rc;
+    TableSpec sp{};
+    sp.out = mem;
+    sp.kind = TABLE_PHASE;
+    sp.nterms = a.nterms;
+    sp.sign = a.sign ? 1 : 0;
+    sp.scale = a.scale;
+    for (int i = 0; i < a.nterms; ++i) sp.terms[i] = a.terms[i];
+    plan.specs.push_back(sp);
+    *tab_out = mem;
+    return PAOS_OK;
+}
+
+// Build the passes for the queued ops.  readout/dst_real: fused read-out for the final pass (0 = none).
+static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int readout, void* dst_real, void* field) {
+    std::vector<Item> th[2];
+    std::vector<GenOp> gens;
+    split_ops(w, ops, th[0], th[1], gens);
+    size_t cur[2] = {0, 0};
+    bool have_src = w->materialized;
+    int axis = 0;
+    int idle = 0;
+    while (cur[0] < th[0].size() || cur[1] < th[1].size()) {
+        std::vector<Item>& mine = th[axis];
+        std::vector<Item>& other = th[1 - axis];
+        size_t& c = cur[axis];
+        size_t& oc = cur[1 - axis];
+        PosAcc acc[KMAX + 1];
+        PassParams P{};
+        P.src = have_src ? field : nullptr;
+        P.dst = field;
+        int pos = 0;
+        bool any = false;
+        while (c < mine.size()) {
+            const Item& it = mine[c];
+            if (is_diag(it)) {
+                if (!acc_item(acc[pos], it)) break;  // table full: end the pass here
+                ++c;
+                any = true;
+            } else if (it.kind == IT_FFT) {
+                if (P.nfft == KMAX) break;
+                P.dir[P.nfft++] = it.dir;
+                ++pos;
+                ++c;
+                any = true;
+            } else {  // barrier: the other thread must have nothing but diagonal items before the same barrier
+                size_t j = oc;
+                while (j < other.size() && is_diag(other[j])) ++j;
+                if (j < other.size() && other[j].kind == IT_BARRIER && other[j].gen == it.gen) {
+                    if (P.ngen == GMAX) break;
+                    GenOp g = gens[it.gen];
+                    g.pos = pos;
+                    P.gen[P.ngen++] = g;
+                    other.erase(other.begin() + j);  // diagonal items before it commute past the barrier
+                    ++c;
+                    any = true;
+                } else {
+                    break;  // the other axis has to catch up first
+                }
+            }
+        }
+        if (!any) {
+            if (++idle > 2) return fail(PAOS_ERR_STATE, "planner made no progress");
+            axis = 1 - axis;
+            continue;
+        }
+        idle = 0;
+        // if this thread is finished and the other one has only diagonal items left, fold them in as a
+        // per-line factor so that no extra sweep is needed
+        if (c == mine.size()) {
+            size_t j = oc;
+            while (j < other.size() && is_diag(other[j])) ++j;
+            if (j == other.size() && oc < other.size()) {
+                PosAcc cross;
+                bool ok = true;
+                for (size_t k = oc; k < other.size() && ok; ++k) ok = acc_item(cross, other[k]);
+                if (ok) {
+                    int rc = spec_from_acc(w, cross, plan, &P.ctab_out);
+                    if (rc) return rc;
+                    oc = other.size();
+                }
+            }
+        }
+        for (int p = 0; p <= P.nfft; ++p) {
+            P.scl[p] = 1.0;
+            P.tab[p] = nullptr;
+            if (acc[p].trivial()) P.scl[p] = acc[p].scale;
+            else {
+                int rc = spec_from_acc(w, acc[p], plan, &P.tab[p]);
+                if (rc) return rc;
+            }
+        }
+        PlannedPass pp;
+        pp.col = axis == 1;
+        pp.P = P;
+        plan.passes.push_back(pp);
+        have_src = true;
+        axis = 1 - axis;
+    }
+    if (plan.passes.empty() && (!w->materialized || readout)) {
+        // nothing queued: materialise the field of ones / run a pure read-out sweep
+        PassParams P{};
+        P.src = w->materialized ? field : nullptr;
+        P.dst = field;
+        P.scl[0] = 1.0;
+        PlannedPass pp;
+        pp.col = false;
+        pp.P = P;
+        plan.passes.push_back(pp);
+    }
+    if (readout && !plan.passes.empty()) {
+        plan.passes.back().P.readout = readout;
+        plan.passes.back().P.dst_real = dst_real;
+    }
+    return PAOS_OK;
+}
+
+static int launch_pass(paos_wfo* w, bool col, const PassParams& P) {
+    cudaEvent_t ea = nullptr, eb = nullptr;
+    if (w->timing) {
+        for (cudaEvent_t* e : {&ea, &eb}) {
+            if (!w->event_pool.empty()) {
+                *e = w->event_pool.back();
+                w->event_pool.pop_back();
+            } else {
+                CU(cudaEventCreate(e));
+            }
+        }
+        CU(cudaEventRecord(ea, w->stream));
+    }
+    cudaError_t e = (w->dtype == PAOS_C128) ? launch_pass_c128(w->n, col, P, w->tw.tw1, w->tw.tw2, w->stream, w->device)
+                                            : launch_pass_c64(w->n, col, P, w->tw.tw1, w->tw.tw2, w->stream, w->device);
+    if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "pass kernel launch failed: %s", cudaGetErrorString(e));
+    if (w->timing) {
+        CU(cudaEventRecord(eb, w->stream));
+        w->timed.push_back(TimedLaunch{ea, eb, P.nfft, col ? 1 : 0});
+    }
+    w->stats.kernel_launches++;
+    w->stats.pass_launches++;
+    w->stats.line_ffts_run += (uint64_t)P.nfft;
+    return PAOS_OK;
+}
+
+static int ensure_pool(paos_wfo* w, size_t need_tables) {
+    const size_t per = (((size_t)w->n * w->elem) + 255) & ~(size_t)255;
+    const size_t need = need_tables * per;
+    if (need <= w->tab_cap) return PAOS_OK;
+    if (w->tab_pool) {
+        CU(cudaStreamSynchronize(w->stream));
+        CU(cudaFree(w->tab_pool));
+        w->tab_pool = nullptr;
+    }
+    size_t cap = need * 2;
+    CU(cudaMalloc((void**)&w->tab_pool, cap));
+    w->tab_cap = cap;
+    return PAOS_OK;
+}
+
+static int run_plan(paos_wfo* w, Plan& plan) {
+    // tables first (one or more launches of the builder), then the passes
+    for (size_t s = 0; s < plan.specs.size(); s += TB_MAX) {
+        TableBlock B{};
+        B.n = w->n;
+        B.dtype = w->dtype;
+        B.ntab = (int)std::min<size_t>(TB_MAX, plan.specs.size() - s);
+        for (int i = 0; i < B.ntab; ++i) B.spec[i] = plan.specs[s + i];
+        cudaError_t e = launch_build_tables(B, w->stream);
+        if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "table builder launch failed: %s", cudaGetErrorString(e));
+        w->stats.kernel_launches++;
+    }
+    for (PlannedPass& pp : plan.passes) {
+        int rc = launch_pass(w, pp.col, pp.P);
+        if (rc) return rc;
+    }
+    return PAOS_OK;
+}
+
+// flush `ops` (a prefix of the queue or all of it)
+static int flush_ops(paos_wfo* w, std::vector<Op>& ops, int readout, void* dst_real) {
+    if (ops.empty() && w->materialized && !readout) return PAOS_OK;
+    int rc = set_device(w);
+    if (rc) return rc;
+    // worst case: every op opens two tables per axis
+    rc = ensure_pool(w, 4 * ops.size() + 8);
+    if (rc) return rc;
+    w->tab_used = 0;
+    Plan plan;
+    // rectangle count tables are TableSpecs too: they were registered when the op was recorded and live in
+    // screens (see paos_wfo_aperture)
+    rc = build_plan(w, ops, plan, readout, dst_real, w->field);
+    if (rc) return rc;
+    rc = run_plan(w, plan);
+    if (rc) return rc;
+    ops.clear();
+    w->materialized = true;
+    return PAOS_OK;
+}
+
+static int flush_all(paos_wfo* w, int readout = 0, void* dst_real = nullptr) {
+    int rc = flush_ops(w, w->ops, readout, dst_real);
+    if (rc) return rc;
+    recycle_screens(w);
+    return PAOS_OK;
+}
+
+static int resolve_timing(paos_wfo* w) {
+    for (TimedLaunch& t : w->timed) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, t.a, t.b));
+        w->timed_ms[t.col][t.nfft] += ms;
+        w->timed_n[t.col][t.nfft] += 1;
+        w->event_pool.push_back(t.a);
+        w->event_pool.push_back(t.b);
+    }
+    w->timed.clear();
+    return PAOS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int paos_abi_version(void) { return PAOS_ABI_VERSION; }
+const char* paos_last_error(void) { return g_last_error.c_str(); }
+
+int paos_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+int paos_wfo_create(paos_wfo** out, int n, int dtype, int device, void* stream, void* borrowed) {
+    if (!out) return fail(PAOS_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (n < 64 || n > 4096 || (n & (n - 1))) return fail(PAOS_ERR_ARG, "grid size %d is not a power of two in [64, 4096]", n);
+    if (dtype != PAOS_C128 && dtype != PAOS_C64) return fail(PAOS_ERR_ARG, "unknown dtype %d", dtype);
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(PAOS_ERR_CUDA, "no CUDA device: libpaos_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return fail(PAOS_ERR_ARG, "device %d out of range (%d devices)", device, count);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(PAOS_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+    CU(cudaSetDevice(device));
+    paos_wfo* w = new paos_wfo();
+    w->n = n;
+    w->dtype = dtype;
+    w->device = device;
+    w->elem = dtype == PAOS_C128 ? 16 : 8;
+    int rc = get_twiddles(device, n, dtype, w->tw);
+    if (rc) {
+        delete w;
+        return rc;
+    }
+    auto bail = [&](cudaError_t e, const char* what) {
+        int r = fail(PAOS_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+        paos_wfo_destroy(w);
+        return r;
+    };
+    cudaError_t e;
+    if (stream) {
+        w->stream = (cudaStream_t)stream;
+    } else {
+        if ((e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+        w->own_stream = true;
+    }
+    if (borrowed) {
+        w->field = borrowed;
+    } else {
+        if ((e = cudaMalloc(&w->field, (size_t)n * n * w->elem)) != cudaSuccess) return bail(e, "cudaMalloc(field)");
+        w->own_field = true;
+    }
+    if ((e = cudaMalloc((void**)&w->partials, paos_wfo::NPARTIALS * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void**)&w->slots, paos_wfo::NSLOTS * 2 * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc");
+    *out = w;
+    return PAOS_OK;
+}
+
+int paos_wfo_destroy(paos_wfo* w) {
+    if (!w) return PAOS_OK;
+    cudaSetDevice(w->device);
+    if (w->stream) cudaStreamSynchronize(w->stream);
+    for (TimedLaunch& t : w->timed) {
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    for (cudaEvent_t e : w->event_pool) cudaEventDestroy(e);
+    for (double* p : w->screens_free) cudaFree(p);
+    for (double* p : w->screens_busy) cudaFree(p);
+    if (w->scratch_field) cudaFree(w->scratch_field);
+    if (w->tab_pool) cudaFree(w->tab_pool);
+    if (w->partials) cudaFree(w->partials);
+    if (w->slots) cudaFree(w->slots);
+    if (w->own_field && w->field) cudaFree(w->field);
+    if (w->own_stream && w->stream) cudaStreamDestroy(w->stream);
+    cudaGetLastError();
+    delete w;
+    return PAOS_OK;
+}
+
+int paos_wfo_reset(paos_wfo* w) {
+    if (!w) return fail(PAOS_ERR_ARG, "null handle");
+    w->ops.clear();
+    recycle_screens(w);
+    w->materialized = false;
+    return PAOS_OK;
+}
+
+int paos_wfo_flush(paos_wfo* w) {
+    if (!w) return fail(PAOS_ERR_ARG, "null handle");
+    return flush_all(w);
+}
+
+int paos_wfo_sync(paos_wfo* w) {
+    if (!w) return fail(PAOS_ERR_ARG, "null handle");
+    int rc = flush_all(w);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(w->stream));
+    return resolve_timing(w);
+}
+
+int paos_wfo_upload(paos_wfo* w, const void* host_src) {
+    if (!w || !host_src) return fail(PAOS_ERR_ARG, "null argument");
+    int rc = set_device(w);
+    if (rc) return rc;
+    w->ops.clear();
+    recycle_screens(w);
+    CU(cudaMemcpyAsync(w->field, host_src, (size_t)w->n * w->n * w->elem, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    w->materialized = true;
+    return PAOS_OK;
+}
+
+int paos_wfo_upload_device(paos_wfo* w, const void* dev_src) {
+    if (!w || !dev_src) return fail(PAOS_ERR_ARG, "null argument");
+    int rc = set_device(w);
+    if (rc) return rc;
+    w->ops.clear();
+    recycle_screens(w);
+    if (dev_src != w->field)
+        CU(cudaMemcpyAsync(w->field, dev_src, (size_t)w->n * w->n * w->elem, cudaMemcpyDeviceToDevice, w->stream));
+    w->materialized = true;
+    return PAOS_OK;
+}
+
+static int read_impl(paos_wfo* w, int what, void* dst, bool to_host) {
+    if (!w || !dst) return fail(PAOS_ERR_ARG, "null argument");
+    if (what < PAOS_READ_WFO || what > PAOS_READ_PSF) return fail(PAOS_ERR_ARG, "unknown read-out %d", what);
+    int rc = set_device(w);
+    if (rc) return rc;
+    const size_t nn = (size_t)w->n * w->n;
+    if (what == PAOS_READ_WFO) {
+        rc = flush_all(w);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(dst, w->field, nn * w->elem, to_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, w->stream));
+    } else {
+        const size_t rbytes = nn * (w->elem / 2);
+        void* dev_out = dst;
+        double* staging = nullptr;
+        if (to_host) {
+            rc = get_screen(w, &staging);
+            if (rc) return rc;
+            dev_out = staging;
+        }
+        if (!w->ops.empty() || !w->materialized) {
+            rc = flush_all(w, what, dev_out);  // read-out fused into the last pass
+            if (rc) return rc;
+        } else {
+            cudaError_t e = launch_readout(w->field, w->n, w->dtype, what, dev_out, w->stream);
+            if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "read-out launch failed: %s", cudaGetErrorString(e));
+            w->stats.kernel_launches++;
+        }
+        if (to_host) {
+            CU(cudaMemcpyAsync(dst, dev_out, rbytes, cudaMemcpyDeviceToHost, w->stream));
+            // flush_all recycled the staging buffer already when it ran; make sure it is not busy-listed twice
+            recycle_screens(w);
+        }
+    }
+    if (to_host) {
+        CU(cudaStreamSynchronize(w->stream));
+        return resolve_timing(w);
+    }
+    return PAOS_OK;
+}
+
+int paos_wfo_read(paos_wfo* w, int what, void* host_dst) { return read_impl(w, what, host_dst, true); }
+int paos_wfo_read_device(paos_wfo* w, int what, void* dev_dst) { return read_impl(w, what, dev_dst, false); }
+
+// ---- elementwise operators -----------------------------------------------------------------------
+static void push_gen(paos_wfo* w, const GenOp& g) {
+    Op op{};
+    op.kind = OP_GEN;
+    op.gen = g;
+    w->ops.push_back(op);
+}
+
+int paos_wfo_aperture(paos_wfo* w, int shape, double ixc, double iyc, double ihx, double ihy, double theta, int obscuration) {
+    if (!w) return fail(PAOS_ERR_ARG, "null handle");
+    if (theta != 0.0) return fail(PAOS_ERR_UNSUPPORTED, "tilted apertures are not implemented (paos/core/run.py:114-121 never tilts)");
+    if (!(ihx > 0.0) || !(ihy > 0.0) || !std::isfinite(ixc) || !std::isfinite(iyc)) return fail(PAOS_ERR_ARG, "bad aperture geometry");
+    GenOp g{};
+    g.flag = obscuration ? 1 : 0;
+    if (shape == PAOS_SHAPE_ELLIPSE) {
+        g.kind = GEN_ELLIPSE;
+        g.p0 = ixc;
+        g.p1 = iyc;
+        g.p2 = 1.0 / ihx;
+        g.p3 = 1.0 / ihy;
+        g.p4 = ihx * ihy;
+    } else if (shape == PAOS_SHAPE_RECT) {
+        // separable 32-sub-pixel counts, built right away into a screen buffer (2*n doubles)
+        int rc = set_device(w);
+        if (rc) return rc;
+        double* buf;
+        rc = get_screen(w, &buf);
+        if (rc) return rc;
+        TableBlock B{};
+        B.n = w->n;
+        B.dtype = w->dtype;
+        B.ntab = 2;
+        B.spec[0].out = buf;
+        B.spec[0].kind = TABLE_COUNT;
+        B.spec[0].cnt_c = ixc;
+        B.spec[0].cnt_full = ihx;
+        B.spec[1].out = buf + w->n;
+        B.spec[1].kind = TABLE_COUNT;
+        B.spec[1].cnt_c = iyc;
+        B.spec[1].cnt_full = ihy;
+        cudaError_t e = launch_build_tables(B, w->stream);
+        if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "table builder launch failed: %s", cudaGetErrorString(e));
+        w->stats.kernel_launches++;
+        g.kind = GEN_RECT;
+        g.ptr0 = buf;
+        g.ptr1 = buf + w->n;
+    } else {
+        return fail(PAOS_ERR_ARG, "unknown aperture shape %d", shape);
+    }
+    push_gen(w, g);
+    return PAOS_OK;
+}
+
+int paos_wfo_make_stop(paos_wfo* w) {
+    if (!w) return fail(PAOS_ERR_ARG, "null handle");
+    int rc = set_device(w);
+    if (rc) return rc;
+    // trailing pointwise operations: unit-modulus ones (signs, phases, screens) do not change the energy, real
+    // masks and earlier stop scalars are folded into the reduction; everything before them is flushed
+    size_t k = w->ops.size();
+    std::vector<GenOp> gens;
+    while (k > 0) {
+        const Op& op = w->ops[k - 1];
+        if (op.kind == OP_SIGN || op.kind == OP_PHASE) {
+            --k;
+        } else if (op.kind == OP_GEN && op.gen.kind == GEN_SCREEN) {
+            --k;
+        } else if (op.kind == OP_GEN && op.gen.kind != GEN_PSD && gens.size() < (size_t)GMAX) {
+            gens.push_back(op.gen);
+            --k;
+        } else {
+            break;
+        }
+    }
+    std::vector<Op> tail(w->ops.begin() + k, w->ops.end());
+    w->ops.resize(k);
+    if (k > 0) {
+        rc = flush_ops(w, w->ops, 0, nullptr);
+        if (rc) return rc;
+    }
+    w->ops = tail;
+    double* slot = w->slots + 2 * (w->slot_next++ % paos_wfo::NSLOTS);
+    cudaError_t e = launch_norm2(w->materialized ? w->field : nullptr, w->n, w->dtype, gens.data(), (int)gens.size(), w->partials,
+                                 paos_wfo::NPARTIALS, slot, w->stream);
+    if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "stop reduction launch failed: %s", cudaGetErrorString(e));
+    w->stats.kernel_launches += 2;
+    GenOp g{};
+    g.kind = GEN_SCALE_DEV;
+    g.ptr0 = slot;
+    push_gen(w, g);
+    return PAOS_OK;
+}
+
+int paos_wfo_quadphase(paos_wfo* w, double c1, double c2, double dx, double dy) {
+    if (!w) return fail(PAOS_ERR_ARG, "null handle");
+    Op op{};
+    op.kind = OP_PHASE;
+    op.tx.kind = op.ty.kind = TERM_QSPACE;
+    op.tx.c1 = op.ty.c1 = c1;
+    op.tx.c2 = op.ty.c2 = c2;
+    op.tx.d = dx;
+    op.ty.d = dy;
+    w->ops.push_back(op);
+    return PAOS_OK;
+}
+
+int paos_wfo_phase_screen_device(paos_wfo* w, const double* dev_screen, double wl) {
+    if (!w || !dev_screen) return fail(PAOS_ERR_ARG, "null argument");
+    GenOp g{};
+    g.kind = GEN_SCREEN;
+    g.ptr0 = dev_screen;
+    g.p0 = wl;
+    push_gen(w, g);
+    return PAOS_OK;
+}
+
+int paos_wfo_phase_screen(paos_wfo* w, const double* host_screen, double wl) {
+    if (!w || !host_screen) return fail(PAOS_ERR_ARG, "null argument");
+    int rc = set_device(w);
+    if (rc) return rc;
+    double* buf;
+    rc = get_screen(w, &buf);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(buf, host_screen, (size_t)w->n * w->n * sizeof(double), cudaMemcpyHostToDevice, w->stream));
+    return paos_wfo_phase_screen_device(w, buf, wl);
+}
+
+static double binom(int n, int k) {
+    double b = 1.0;
+    for (int i = 1; i <= k; ++i) b = b * (double)(n - k + i) / (double)i;
+    return b;
+}
+
+int paos_wfo_zernike(paos_wfo* w, int nterms, const int* m, const int* n, const double* coef, double radius, double dx,
+                     double dy, double offset, int origin, double wl, double* wfe_host_out) {
+    if (!w || !m || !n || !coef) return fail(PAOS_ERR_ARG, "null argument");
+    if (nterms < 1) return fail(PAOS_ERR_ARG, "need at least one Zernike term");
+    if (origin != 0 && origin != 1) return fail(PAOS_ERR_ARG, "origin must be 0 ('x') or 1 ('y')");
+    if (!(radius > 0.0)) return fail(PAOS_ERR_ARG, "radius must be positive");
+    int rc = set_device(w);
+    if (rc) return rc;
+    double* screen;
+    rc = get_screen(w, &screen);
+    if (rc) return rc;
+    for (int s = 0; s < nterms; s += ZERN_MAX) {
+        ZernParams Z{};
+        Z.K = std::min(ZERN_MAX, nterms - s);
+        Z.origin = origin;
+        Z.n = w->n;
+        Z.accumulate = s > 0;
+        Z.radius = radius;
+        Z.dx = dx;
+        Z.dy = dy;
+        Z.cos_off = std::cos(offset);
+        Z.sin_off = std::sin(offset);
+        for (int k = 0; k < Z.K; ++k) {
+            const int mm = m[s + k], nn = n[s + k], am = mm < 0 ? -mm : mm;
+            if (nn < am || ((nn - am) & 1)) return fail(PAOS_ERR_ARG, "invalid Zernike (m, n) = (%d, %d)", mm, nn);
+            const int kr = (nn - am) / 2;
+            Z.m[k] = mm;
+            Z.nn[k] = nn;
+            // scipy's eval_jacobi returns binom(k+alpha, k) * recurrence; (-1)^k from zernike.py:245-247
+            Z.coef[k] = coef[s + k] * binom(kr + am, kr) * ((kr & 1) ? -1.0 : 1.0);
+        }
+        cudaError_t e = launch_zernike(Z, screen, w->stream);
+        if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "zernike launch failed: %s", cudaGetErrorString(e));
+        w->stats.kernel_launches++;
+    }
+    if (wfe_host_out) {
+        CU(cudaMemcpyAsync(wfe_host_out, screen, (size_t)w->n * w->n * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+    }
+    return paos_wfo_phase_screen_device(w, screen, wl);
+}
+
+// run a private op list on the scratch field (PSD synthesis) without touching the handle's queue
+static int run_on_scratch(paos_wfo* w, std::vector<Op>& ops) {
+    int rc = ensure_pool(w, 4 * (ops.size() + w->ops.size()) + 16);
+    if (rc) return rc;
+    // the handle's own queue has not been planned yet, so the pool can be used from the start; the tables of
+    // this private plan are consumed before any later flush rewrites them (stream order)
+    w->tab_used = 0;
+    Plan plan;
+    const bool mat = w->materialized;
+    w->materialized = true;  // the scratch field has data
+    rc = build_plan(w, ops, plan, 0, nullptr, w->scratch_field);
+    w->materialized = mat;
+    if (rc) return rc;
+    return run_plan(w, plan);
+}
+
+int paos_wfo_psd(paos_wfo* w, double A, double B, double C, double fknee, double fmin, double fmax, double SR,
+                 double unit_scale, double dx, double dy, double wl, const double* noise1, const double* noise2,
+                 uint64_t seed, double* wfe_host_out) {
+    if (!w) return fail(PAOS_ERR_ARG, "null handle");
+    if ((noise1 == nullptr) != (noise2 == nullptr)) return fail(PAOS_ERR_ARG, "pass both noise arrays or neither");
+    int rc = set_device(w);
+    if (rc) return rc;
+    const size_t nn = (size_t)w->n * w->n;
+    double *d1, *d2, *screen;
+    if ((rc = get_screen(w, &d1)) || (rc = get_screen(w, &d2)) || (rc = get_screen(w, &screen))) return rc;
+    if (noise1) {
+        CU(cudaMemcpyAsync(d1, noise1, nn * sizeof(double), cudaMemcpyHostToDevice, w->stream));
+        CU(cudaMemcpyAsync(d2, noise2, nn * sizeof(double), cudaMemcpyHostToDevice, w->stream));
+    } else {
+        cudaError_t e = launch_normal(seed, 1u, w->n, d1, w->stream);
+        if (e == cudaSuccess) e = launch_normal(seed, 2u, w->n, d2, w->stream);
+        if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "noise launch failed: %s", cudaGetErrorString(e));
+        w->stats.kernel_launches += 2;
+    }
+    if (!w->scratch_field) CU(cudaMalloc(&w->scratch_field, nn * w->elem));
+    cudaError_t e = launch_real_to_complex(d1, w->n, w->dtype, w->scratch_field, w->stream);
+    if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "launch failed: %s", cudaGetErrorString(e));
+    w->stats.kernel_launches++;
+    // F = fft2(noise) * filter ; wfe = real(ifft2(F)) (numpy default normalisation: 1/(N*N) on the inverse)
+    std::vector<Op> ops;
+    Op f{};
+    f.kind = OP_FFT_RAW;
+    f.dir = +1;
+    f.raw_scale = 1.0;
+    ops.push_back(f);
+    Op g{};
+    g.kind = OP_GEN;
+    g.gen.kind = GEN_PSD;
+    g.gen.p0 = A;
+    g.gen.p1 = B;
+    g.gen.p2 = C;
+    g.gen.p3 = fknee;
+    g.gen.p4 = fmin;
+    g.gen.p5 = fmax;
+    g.gen.p6 = 1.0 / ((double)w->n * dx);
+    g.gen.p7 = 1.0 / ((double)w->n * dy);
+    g.gen.p8 = (double)w->n;
+    ops.push_back(g);
+    f.dir = -1;
+    ops.push_back(f);
+    rc = run_on_scratch(w, ops);
+    if (rc) return rc;
+    e = launch_psd_finalize(w->scratch_field, w->n, w->dtype, d2, SR, unit_scale, screen, w->stream);
+    if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "launch failed: %s", cudaGetErrorString(e));
+    w->stats.kernel_launches++;
+    w->stats.fft2_recorded += 2;
+    if (wfe_host_out) {
+        CU(cudaMemcpyAsync(wfe_host_out, screen, nn * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+    }
+    return paos_wfo_phase_screen_device(w, screen, wl);
+}
+
+// ---- propagators ---------------------------------------------------------------------------------
+static void push_sign(paos_wfo* w) {
+    Op op{};
+    op.kind = OP_SIGN;
+    w->ops.push_back(op);
+}
+static void push_fft(paos_wfo* w, int dir) {
+    Op op{};
+    op.kind = OP_FFT;
+    op.dir = dir;
+    w->ops.push_back(op);
+    w->stats.fft2_recorded++;
+}
+static void push_phase(paos_wfo* w, int kind, double c1, double c2, double dx, double dy) {
+    Op op{};
+    op.kind = OP_PHASE;
+    op.tx.kind = op.ty.kind = kind;
+    op.tx.c1 = op.ty.c1 = c1;
+    op.tx.c2 = op.ty.c2 = c2;
+    op.tx.d = dx;
+    op.ty.d = dy;
+    w->ops.push_back(op);
+}
+
+static int check_prop(paos_wfo* w, double wl, double dz, double dx, double dy) {
+    if (!w) return fail(PAOS_ERR_ARG, "null handle");
+    if (!(wl > 0.0) || !(dx > 0.0) || !(dy > 0.0) || !std::isfinite(dz) || dz == 0.0) return fail(PAOS_ERR_ARG, "bad propagation scalars");
+    return PAOS_OK;
+}
+
+int paos_wfo_ptp(paos_wfo* w, double wl, double dz, double dx, double dy) {
+    int rc = check_prop(w, wl, dz, dx, dy);
+    if (rc) return rc;
+    const double c = (M_PI * wl) * dz;  // numpy: (np.pi * wl * dz), left to right
+    push_sign(w);
+    push_fft(w, +1);
+    push_phase(w, TERM_QFREQ, -1.0, c, dx, dy);
+    push_fft(w, -1);
+    push_sign(w);
+    return PAOS_OK;
+}
+
+int paos_wfo_stw(paos_wfo* w, double wl, double dz, double dx, double dy) {
+    int rc = check_prop(w, wl, dz, dx, dy);
+    if (rc) return rc;
+    const double c = (M_PI * wl) * dz;
+    push_sign(w);
+    push_fft(w, dz >= 0 ? +1 : -1);
+    push_phase(w, TERM_QFREQ, 1.0, c, dx, dy);
+    push_sign(w);
+    return PAOS_OK;
+}
+
+int paos_wfo_wts(paos_wfo* w, double wl, double dz, double dx, double dy) {
+    int rc = check_prop(w, wl, dz, dx, dy);
+    if (rc) return rc;
+    const double c = M_PI / (dz * wl);
+    push_phase(w, TERM_QSPACE, 1.0, c, dx, dy);
+    push_sign(w);
+    push_fft(w, dz >= 0 ? +1 : -1);
+    push_sign(w);
+    return PAOS_OK;
+}
+
+int paos_wfo_fft2(paos_wfo* w, int inverse) {
+    if (!w) return fail(PAOS_ERR_ARG, "null handle");
+    push_sign(w);
+    push_fft(w, inverse ? -1 : +1);
+    push_sign(w);
+    return PAOS_OK;
+}
+
+// ---- statistics ----------------------------------------------------------------------------------
+int paos_wfo_stats(paos_wfo* w, paos_stats* out) {
+    if (!w || !out) return fail(PAOS_ERR_ARG, "null argument");
+    *out = w->stats;
+    return PAOS_OK;
+}
+
+int paos_wfo_enable_timing(paos_wfo* w, int enable) {
+    if (!w) return fail(PAOS_ERR_ARG, "null handle");
+    w->timing = enable != 0;
+    return PAOS_OK;
+}
+
+int paos_wfo_timing(paos_wfo* w, double* pass_ms, uint64_t* pass_launches) {
+    if (!w) return fail(PAOS_ERR_ARG, "null handle");
+    double ms = 0.0;
+    uint64_t n = 0;
+    for (int c = 0; c < 2; ++c)
+        for (int k = 0; k <= KMAX; ++k) {
+            ms += w->timed_ms[c][k];
+            n += w->timed_n[c][k];
+        }
+    if (pass_ms) *pass_ms = ms;
+    if (pass_launches) *pass_launches = n;
+    return PAOS_OK;
+}
+
+int paos_wfo_timing_detail(paos_wfo* w, int col, int nfft, double* ms, uint64_t* launches, int reset) {
+    if (!w) return fail(PAOS_ERR_ARG, "null handle");
+    if (col < 0 || col > 1 || nfft < 0 || nfft > KMAX) return fail(PAOS_ERR_ARG, "bad timing bucket");
+    if (ms) *ms = w->timed_ms[col][nfft];
+    if (launches) *launches = w->timed_n[col][nfft];
+    if (reset) {
+        w->timed_ms[col][nfft] = 0.0;
+        w->timed_n[col][nfft] = 0;
+    }
+    return PAOS_OK;
+}
+
+}  // extern "C"
