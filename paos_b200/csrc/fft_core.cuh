@@ -44,6 +44,20 @@ template <typename R> __device__ __forceinline__ C<R> ldc_ro(const C<R>* p) {
     V v = __ldg(reinterpret_cast<const V*>(p));
     return C<R>(v.x, v.y);
 }
+// streaming (evict-first) access for the wavefront itself: it is touched once per pass and must not push
+// the twiddle and phase tables out of L1/L2
+template <typename R> __device__ __forceinline__ C<R> ldc_stream(const C<R>* p) {
+    typedef typename cx2<R>::type V;
+    V v = __ldcs(reinterpret_cast<const V*>(p));
+    return C<R>(v.x, v.y);
+}
+template <typename R> __device__ __forceinline__ void stc_stream(C<R>* p, C<R> a) {
+    typedef typename cx2<R>::type V;
+    V v;
+    v.x = a.x;
+    v.y = a.y;
+    __stcs(reinterpret_cast<V*>(p), v);
+}
 template <typename R> __device__ __forceinline__ void stc(C<R>* p, C<R> a) {
     typedef typename cx2<R>::type V;
     V v;

@@ -92,43 +92,54 @@ static __device__ __noinline__ double psd_filter(const GenOp& g, int ix, int iy)
 }
 
 // |.|, angle or |.|^2 of one element (what = PAOS_READ_AMPLITUDE / _PHASE / _PSF)
-template <typename R> __device__ __forceinline__ R readout_value(C<R> v, int what) {
+template <typename R> __device__ __noinline__ R readout_value(C<R> v, int what) {
     if (what == 1) return (R)hypot((double)v.x, (double)v.y);
     if (what == 2) return (R)atan2((double)v.y, (double)v.x);
     return v.x * v.x + v.y * v.y;
 }
 
-// real or complex factor of a general op at pixel (ix, iy); returns false when the factor is exactly 1
-template <typename R>
-__device__ __forceinline__ void apply_gen(C<R>& v, const GenOp& g, int ix, int iy, int n) {
+// Slow path of one general factor at pixel (ix, iy): exact edge-pixel overlap, phase screens, the PSD filter.
+// Out of line on purpose: this is cold code next to the line FFT, and inlining it per register element made
+// the kernel 250 KB of SASS.  Returns the complex factor (fr, fi).
+static __device__ __noinline__ void gen_factor_slow(const GenOp& g, int ix, int iy, int n, double& fr, double& fi) {
+    double re = 1.0, im = 0.0;
     switch (g.kind) {
         case GEN_ELLIPSE: {
             double m = ellipse_fraction(g, (double)ix, (double)iy);
-            if (g.flag) m = 1.0 - m;
-            v = v * (R)m;
+            re = g.flag ? 1.0 - m : m;
+        } break;
+        case GEN_SCREEN: {
+            const double w = __ldg((const double*)g.ptr0 + (size_t)iy * n + ix);
+            if (w != 0.0) sincos((6.283185307179586 * w) / g.p0, &im, &re);
+        } break;
+        case GEN_PSD: re = psd_filter(g, ix, iy); break;
+        default: break;
+    }
+    fr = re;
+    fi = im;
+}
+
+// single-op version used by the stop reduction (aux_kernels.cu)
+template <typename R>
+__device__ __forceinline__ void apply_gen(C<R>& v, const GenOp& g, int ix, int iy, int n) {
+    PassParams* none = nullptr;
+    (void)none;
+    double re = 1.0, im = 0.0;
+    switch (g.kind) {
+        case GEN_ELLIPSE: {
+            double m = ellipse_fraction(g, (double)ix, (double)iy);
+            re = g.flag ? 1.0 - m : m;
         } break;
         case GEN_RECT: {
             const double cx = __ldg((const double*)g.ptr0 + ix), cy = __ldg((const double*)g.ptr1 + iy);
             double m = (cy * cx) / 1024.0;
-            if (g.flag) m = 1.0 - m;
-            v = v * (R)m;
+            re = g.flag ? 1.0 - m : m;
         } break;
-        case GEN_SCREEN: {
-            const double w = __ldg((const double*)g.ptr0 + (size_t)iy * n + ix);
-            if (w != 0.0) {
-                double s, c;
-                sincos((6.283185307179586 * w) / g.p0, &s, &c);
-                v = v * C<R>((R)c, (R)s);
-            }
-        } break;
-        case GEN_SCALE_DEV: {
-            v = v * (R)__ldg((const double*)g.ptr0);
-        } break;
-        case GEN_PSD: {
-            v = v * (R)psd_filter(g, ix, iy);
-        } break;
+        case GEN_SCALE_DEV: re = __ldg((const double*)g.ptr0); break;
         default: break;
     }
+    (void)im;
+    v = v * (R)re;
 }
 
 // ---- the pass kernel ---------------------------------------------------------------------------------
@@ -157,20 +168,66 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
         for (int j = 0; j < E; ++j) {
             const int idx = t + j * T;
             const size_t ga = COL ? ((size_t)idx * N + line) : ((size_t)line * N + idx);
-            v[j] = ldc(src + ga);
+            v[j] = ldc_stream(src + ga);
         }
     } else {
 #pragma unroll
         for (int j = 0; j < E; ++j) v[j] = C<R>((R)1, (R)0);
     }
 
-    auto diag = [&](int pos) {
-        for (int g = 0; g < P.ngen; ++g) {
-            if (P.gen[g].pos != pos) continue;
+    if (P.ctab_in) {
+        const C<R> c = ldc_ro(reinterpret_cast<const C<R>*>(P.ctab_in) + line);
 #pragma unroll
-            for (int j = 0; j < E; ++j) {
-                const int idx = t + j * T;
-                apply_gen(v[j], P.gen[g], COL ? line : idx, COL ? idx : line, N);
+        for (int j = 0; j < E; ++j) v[j] = v[j] * c;
+    }
+    for (int pos = 0;; ++pos) {
+        // diagonal factors of this position: general (masks, screens, stop scalar), then the along-line table
+        if (P.genmask >> pos & 1) {
+            for (int gi = 0; gi < P.ngen; ++gi) {
+                const GenOp& g = P.gen[gi];
+                if (g.pos != pos) continue;
+                if (g.kind == GEN_ELLIPSE) {
+                    // interior / exterior pixels are classified inline (p5, p6 = squared radii of the bands in
+                    // which a pixel is certainly inside / outside); only edge pixels take the exact routine
+                    const double inside = g.flag ? 0.0 : 1.0, outside = g.flag ? 1.0 : 0.0;
+#pragma unroll
+                    for (int j = 0; j < E; ++j) {
+                        const int idx = t + j * T;
+                        const int ix = COL ? line : idx, iy = COL ? idx : line;
+                        const double u = ((double)ix - g.p0) * g.p2, w2 = ((double)iy - g.p1) * g.p3;
+                        const double r2 = u * u + w2 * w2;
+                        double m;
+                        if (r2 <= g.p5) m = inside;
+                        else if (r2 >= g.p6) m = outside;
+                        else {
+                            double fi;
+                            gen_factor_slow(g, ix, iy, N, m, fi);
+                        }
+                        v[j] = v[j] * (R)m;
+                    }
+                } else if (g.kind == GEN_RECT) {
+#pragma unroll
+                    for (int j = 0; j < E; ++j) {
+                        const int idx = t + j * T;
+                        const double cx = __ldg((const double*)g.ptr0 + (COL ? line : idx));
+                        const double cy = __ldg((const double*)g.ptr1 + (COL ? idx : line));
+                        double m = (cy * cx) / 1024.0;
+                        if (g.flag) m = 1.0 - m;
+                        v[j] = v[j] * (R)m;
+                    }
+                } else if (g.kind == GEN_SCALE_DEV) {
+                    const R m = (R)__ldg((const double*)g.ptr0);
+#pragma unroll
+                    for (int j = 0; j < E; ++j) v[j] = v[j] * m;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < E; ++j) {
+                        const int idx = t + j * T;
+                        double fr, fi;
+                        gen_factor_slow(g, COL ? line : idx, COL ? idx : line, N, fr, fi);
+                        v[j] = v[j] * C<R>((R)fr, (R)fi);
+                    }
+                }
             }
         }
         const C<R>* tab = reinterpret_cast<const C<R>*>(P.tab[pos]);
@@ -184,16 +241,8 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
                 for (int j = 0; j < E; ++j) v[j] = v[j] * s;
             }
         }
-    };
-
-    if (P.ctab_in) {
-        const C<R> c = ldc_ro(reinterpret_cast<const C<R>*>(P.ctab_in) + line);
-#pragma unroll
-        for (int j = 0; j < E; ++j) v[j] = v[j] * c;
-    }
-    diag(0);
-    for (int k = 0; k < P.nfft; ++k) {
-        const bool inv = P.dir[k] < 0;
+        if (pos == P.nfft) break;
+        const bool inv = P.dir[pos] < 0;
         if (inv) {
 #pragma unroll
             for (int j = 0; j < E; ++j) v[j] = C<R>(v[j].y, v[j].x);
@@ -203,7 +252,6 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
 #pragma unroll
             for (int j = 0; j < E; ++j) v[j] = C<R>(v[j].y, v[j].x);
         }
-        diag(k + 1);
     }
     if (P.ctab_out) {
         const C<R> c = ldc_ro(reinterpret_cast<const C<R>*>(P.ctab_out) + line);
@@ -215,7 +263,7 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
     for (int j = 0; j < E; ++j) {
         const int idx = t + j * T;
         const size_t ga = COL ? ((size_t)idx * N + line) : ((size_t)line * N + idx);
-        stc(dst + ga, v[j]);
+        stc_stream(dst + ga, v[j]);
     }
     if (P.readout) {
         // fused read-out (wfo.py:167-172, plot.py:125-130) so a snapshot costs no extra sweep

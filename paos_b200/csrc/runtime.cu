@@ -347,6 +347,7 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
                     GenOp g = gens[it.gen];
                     g.pos = pos;
                     P.gen[P.ngen++] = g;
+                    P.genmask |= 1u << pos;
                     other.erase(other.begin() + j);  // diagonal items before it commute past the barrier
                     ++c;
                     any = true;
@@ -714,6 +715,11 @@ int paos_wfo_aperture(paos_wfo* w, int shape, double ixc, double iyc, double ihx
         g.p2 = 1.0 / ihx;
         g.p3 = 1.0 / ihy;
         g.p4 = ihx * ihy;
+        // a unit pixel lies within d = half its diagonal (in the frame where the ellipse is the unit circle) of its
+        // centre: certainly inside when r <= 1 - d, certainly outside when r >= 1 + d (plus a rounding margin)
+        const double d = 0.5 * std::sqrt(g.p2 * g.p2 + g.p3 * g.p3) * (1.0 + 1e-9) + 1e-12;
+        g.p5 = d < 1.0 ? (1.0 - d) * (1.0 - d) : -1.0;
+        g.p6 = (1.0 + d) * (1.0 + d);
     } else if (shape == PAOS_SHAPE_RECT) {
         // separable 32-sub-pixel counts, built right away into a screen buffer (2*n doubles)
         int rc = set_device(w);

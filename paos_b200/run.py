@@ -45,21 +45,26 @@ def _surface_aperture(wfo, item, vt, vs):
 
 
 def run(pupil_diameter, wavelength, gridsize, zoom, field, opt_chain, *, device=0, dtype="complex128",
-        stream=None, keys=None, psd_noise=None, wfo_out=None):
+        stream=None, keys=None, psd_noise=None, wfo=None, snapshot=None):
     """Run the physical-optics propagation of one wavelength / field through ``opt_chain``.
 
     Positional parameters and the returned ``{surface_num: {...}}`` dictionary are the reference's.  Keyword-only
     extras: ``device``/``dtype``/``stream`` are passed to :class:`WFO`; ``keys`` limits the arrays read back per
     saved surface (e.g. ``("amplitude",)``, the reference pipeline's ``store_keys``); ``psd_noise`` is a callable
-    ``(surface_num, shape) -> (n1, n2)`` injecting the PSD noise draws (bit-parity mode); ``wfo_out`` is an
-    optional list that receives the final :class:`WFO` (to keep results on the device).
+    ``(surface_num, shape) -> (n1, n2)`` injecting the PSD noise draws (bit-parity mode); ``wfo`` re-uses an
+    existing :class:`WFO` (its buffer and stream) instead of allocating one; ``snapshot`` replaces
+    :func:`push_results` for saved surfaces, e.g. to keep read-outs on the device (``snapshot(wfo, item) -> dict``).
     """
     assert isinstance(opt_chain, dict), "opt_chain must be a dict"
     results = {}
     vt = np.array([0.0, field["ut"]])
     vs = np.array([0.0, field["us"]])
     total_t, total_s = ABCD(), ABCD()
-    wfo = WFO(pupil_diameter, wavelength, gridsize, zoom, device=device, dtype=dtype, stream=stream)
+    if wfo is None:
+        wfo = WFO(pupil_diameter, wavelength, gridsize, zoom, device=device, dtype=dtype, stream=stream)
+    else:
+        assert wfo.grid_size == gridsize, "the re-used WFO has a different grid size"
+        wfo.reset(pupil_diameter, wavelength, zoom)
 
     for item in opt_chain.values():
         if item["type"] == "Coordinate Break":
@@ -94,7 +99,7 @@ def run(pupil_diameter, wavelength, gridsize, zoom, field, opt_chain, *, device=
                 snap["wfe"] = wfe
 
         if save:
-            snap.update(push_results(wfo, keys))
+            snap.update(push_results(wfo, keys) if snapshot is None else snapshot(wfo, item))
 
         abcd_t, abcd_s = item["ABCDt"], item["ABCDs"]
         Ms, Mt = abcd_s.M, abcd_t.M
@@ -116,8 +121,6 @@ def run(pupil_diameter, wavelength, gridsize, zoom, field, opt_chain, *, device=
         total_s = abcd_s * total_s
         if save:
             snap["ABCDt"], snap["ABCDs"] = total_t, total_s
-            results[item["num"]] = deepcopy(snap)
+            results[item["num"]] = deepcopy(snap) if snapshot is None else snap
 
-    if wfo_out is not None:
-        wfo_out.append(wfo)
     return results

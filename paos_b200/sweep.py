@@ -1,0 +1,161 @@
+"""Batch front-end: run many independent propagations on one GPU, or shard them over the GPUs of a box.
+
+Replaces the reference's ``joblib.Parallel`` fan-out over wavelengths (``paos/core/pipeline.py:140-150``).
+Jobs (see ``paos_b200/configs.py``) are independent, so the only parallel structure is:
+
+* inside a GPU: a few *slots*, each a persistent :class:`WFO` on its own CUDA stream.  The host plans job k+1
+  (pure scalar work) while the device still executes job k; the image-plane read-out of every job lands in a
+  device stack, and (``host=True``) is copied to pinned host memory on the same stream, overlapping the next job;
+* across GPUs: one process per GPU (``torch.distributed``), contiguous cost-balanced blocks of the job list per
+  rank, no communication during propagation, and ONE gather of the result stack at the end
+  (:func:`gather_stack`, NCCL over NVLink on GPUs, gloo in the CPU tests).
+"""
+import numpy as np
+
+from . import _lib
+from .run import run
+from .wfo import WFO
+
+READS = {"amplitude": _lib.READ_AMPLITUDE, "psf": _lib.READ_PSF, "phase": _lib.READ_PHASE}
+
+
+def job_cost(job):
+    """Relative cost of a job: number of surfaces that propagate (each costs 1-2 FFT2)."""
+    return sum(1 for it in job["opt_chain"].values()
+               if np.isfinite(it["ABCDt"].thickness) and abs(it["ABCDt"].thickness) > 1e-10) or 1
+
+
+def partition(jobs, world_size):
+    """Contiguous, cost-balanced split of ``jobs`` into ``world_size`` blocks -> list of (start, stop)."""
+    n = len(jobs)
+    cost = np.array([job_cost(j) for j in jobs], dtype=np.float64)
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    bounds = [0]
+    for r in range(1, world_size):
+        target = cum[-1] * r / world_size
+        k = int(np.searchsorted(cum, target, side="left"))
+        k = min(max(k, bounds[-1]), n)
+        bounds.append(k)
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
+
+
+class Sweep:
+    """Persistent executor for jobs of one grid size on one GPU."""
+
+    def __init__(self, gridsize, device=0, dtype="complex128", slots=3, what="psf"):
+        import torch
+
+        if what not in READS:
+            raise ValueError(f"what must be one of {sorted(READS)}")
+        self.n = int(gridsize)
+        self.device = int(device)
+        self.dtype = dtype
+        self.what = what
+        self.torch = torch
+        self.tdev = torch.device("cuda", self.device)
+        self.rdtype = torch.float64 if dtype == "complex128" else torch.float32
+        self.streams = [torch.cuda.Stream(device=self.tdev) for _ in range(slots)]
+        self.wfos = [WFO(1.0, 1.0e-6, self.n, 1.0, device=self.device, dtype=dtype, stream=s) for s in self.streams]
+        self.events = [None] * slots
+
+    def empty_stack(self, count, host=False):
+        torch = self.torch
+        if host:
+            return torch.empty((count, self.n, self.n), dtype=self.rdtype, pin_memory=True)
+        return torch.empty((count, self.n, self.n), dtype=self.rdtype, device=self.tdev)
+
+    def run(self, jobs, out=None, host_out=None, psd_noise=None):
+        """Propagate ``jobs``; the last saved surface of job k is read out (``what``) into ``out[k]``.
+
+        ``out``: device stack (allocated when None).  ``host_out``: optional pinned host stack that also receives
+        every result (asynchronous device-to-host copies inside the pipeline).  Returns ``(out, meta)`` with one
+        ``meta`` dict of host scalars per job.  The call returns after all device work has completed.
+        """
+        import ctypes as C
+
+        torch = self.torch
+        if out is None:
+            out = self.empty_stack(len(jobs))
+        code = READS[self.what]
+        meta = []
+        nslots = len(self.wfos)
+        for k, job in enumerate(jobs):
+            s = k % nslots
+            wfo, stream = self.wfos[s], self.streams[s]
+            dst = out[k]
+
+            def snapshot(w, item, dst=dst):
+                _lib.check(_lib.lib.paos_wfo_read_device(w._handle, code, C.c_void_p(dst.data_ptr())))
+                return dict(wz=w.wz, distancetofocus=w.distancetofocus, fratio=w.fratio, dx=w.dx, dy=w.dy, wl=w.wl,
+                            extent=w.extent, propagator=w.propagator)
+
+            noise = None
+            if psd_noise is not None:
+                noise = psd_noise(job)
+            res = run(job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"],
+                      job["opt_chain"], wfo=wfo, snapshot=snapshot, psd_noise=noise)
+            last = res[max(res.keys())] if res else {}
+            last = {k2: v for k2, v in last.items() if k2 not in ("aperture", "wfe")}
+            last["tag"] = job.get("tag", str(k))
+            meta.append(last)
+            if host_out is not None:
+                with torch.cuda.stream(stream):
+                    host_out[k].copy_(dst, non_blocking=True)
+        for stream in self.streams:
+            stream.synchronize()
+        return out, meta
+
+    def stats(self):
+        tot = {}
+        for w in self.wfos:
+            for k, v in w.stats().items():
+                tot[k] = tot.get(k, 0) + v
+        return tot
+
+    def enable_timing(self, on=True):
+        for w in self.wfos:
+            _lib.check(_lib.lib.paos_wfo_enable_timing(w._handle, 1 if on else 0))
+
+    def timing_detail(self, reset=True):
+        """{(col, nfft): (ms, launches)} summed over the slots."""
+        import ctypes as C
+
+        out = {}
+        for w in self.wfos:
+            _lib.check(_lib.lib.paos_wfo_sync(w._handle))
+            for col in (0, 1):
+                for nfft in range(0, 9):
+                    ms, cnt = C.c_double(), C.c_uint64()
+                    _lib.check(_lib.lib.paos_wfo_timing_detail(w._handle, col, nfft, C.byref(ms), C.byref(cnt), 1 if reset else 0))
+                    if cnt.value:
+                        a = out.get((col, nfft), (0.0, 0))
+                        out[(col, nfft)] = (a[0] + ms.value, a[1] + cnt.value)
+        return out
+
+
+def gather_stack(local, counts, dst=0, group=None):
+    """Gather per-rank stacks ``[n_local, N, N]`` on rank ``dst`` (the single collective of a sweep).
+
+    ``counts``: jobs per rank (ragged blocks are padded to the largest count for the collective).  Returns the
+    concatenated stack on ``dst`` and ``None`` elsewhere.  Works with NCCL (CUDA tensors) and gloo (CPU tensors).
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1:
+        return local
+    width = max(counts)
+    pad = local
+    if local.shape[0] != width:
+        pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+    pad = pad.contiguous()
+    if rank == dst:
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.gather(pad, gather_list=bufs, dst=dst, group=group)
+        return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+    dist.gather(pad, gather_list=None, dst=dst, group=group)
+    return None

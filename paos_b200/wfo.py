@@ -36,11 +36,42 @@ class WFO:
     """
 
     def __init__(self, beam_diameter, wl, grid_size, zoom, *, device=0, dtype="complex128", stream=None):
+        self._handle = None
+        self._set_beam(beam_diameter, wl, grid_size, zoom)
+        self._n = int(grid_size)
+        if dtype in ("complex128", np.complex128):
+            self._code, self._cdtype, self._rdtype = _lib.PAOS_C128, np.complex128, np.float64
+        elif dtype in ("complex64", np.complex64):
+            self._code, self._cdtype, self._rdtype = _lib.PAOS_C64, np.complex64, np.float32
+        else:
+            raise ValueError(f"dtype {dtype!r} not supported (complex128 or complex64)")
+        self.dtype = "complex128" if self._code == _lib.PAOS_C128 else "complex64"
+        if _lib.device_count() == 0:
+            raise _lib.PaosCudaError("no usable sm_100 (B200) device: paos_b200 has no CPU fallback")
+        torch = _torch()
+        self._device = int(device)
+        self._tdev = torch.device("cuda", self._device)
+        if stream is None:
+            stream = torch.cuda.current_stream(self._tdev)
+            if stream.cuda_stream == 0:
+                # the legacy default stream cannot be named through the C ABI (NULL = "library-owned stream");
+                # give the wavefront its own stream and fence device read-outs against the caller's stream
+                stream = torch.cuda.Stream(device=self._tdev)
+        self._stream = stream
+        tdt = torch.complex128 if self._code == _lib.PAOS_C128 else torch.complex64
+        with torch.cuda.stream(self._stream):
+            self._buf = torch.empty((self._n, self._n), dtype=tdt, device=self._tdev)
+        h = C.c_void_p()
+        check(lib.paos_wfo_create(C.byref(h), self._n, self._code, self._device,
+                                  C.c_void_p(self._stream.cuda_stream), C.c_void_p(self._buf.data_ptr())))
+        self._handle = h
+
+    def _set_beam(self, beam_diameter, wl, grid_size, zoom):
+        """Scalar state of a fresh wavefront (``wfo.py:99-120``)."""
         assert np.log2(grid_size).is_integer(), "Grid size should be 2**n"
         assert zoom > 0, "zoom factor should be positive"
         assert beam_diameter > 0, "beam diameter should be positive"
         assert wl > 0, "a wavelength should be positive"
-        self._handle = None
         self._wl = wl
         self._z = 0.0
         self._w0 = beam_diameter / 2.0
@@ -53,26 +84,12 @@ class WFO:
         self._fratio = np.inf
         self._zoom = zoom
         self._propagator = ""
-        self._n = int(grid_size)
-        if dtype in ("complex128", np.complex128):
-            self._code, self._cdtype, self._rdtype = _lib.PAOS_C128, np.complex128, np.float64
-        elif dtype in ("complex64", np.complex64):
-            self._code, self._cdtype, self._rdtype = _lib.PAOS_C64, np.complex64, np.float32
-        else:
-            raise ValueError(f"dtype {dtype!r} not supported (complex128 or complex64)")
-        if _lib.device_count() == 0:
-            raise _lib.PaosCudaError("no usable sm_100 (B200) device: paos_b200 has no CPU fallback")
-        torch = _torch()
-        self._device = int(device)
-        self._tdev = torch.device("cuda", self._device)
-        self._stream = stream if stream is not None else torch.cuda.current_stream(self._tdev)
-        tdt = torch.complex128 if self._code == _lib.PAOS_C128 else torch.complex64
-        with torch.cuda.stream(self._stream):
-            self._buf = torch.empty((self._n, self._n), dtype=tdt, device=self._tdev)
-        h = C.c_void_p()
-        check(lib.paos_wfo_create(C.byref(h), self._n, self._code, self._device,
-                                  C.c_void_p(self._stream.cuda_stream), C.c_void_p(self._buf.data_ptr())))
-        self._handle = h
+
+    def reset(self, beam_diameter, wl, zoom):
+        """Start a new chain on the same device buffer (extension: avoids re-allocating per propagation)."""
+        self._set_beam(beam_diameter, wl, self._n, zoom)
+        check(lib.paos_wfo_reset(self._handle))
+        return self
 
     def __del__(self):
         h, self._handle = getattr(self, "_handle", None), None
@@ -124,6 +141,7 @@ class WFO:
         with torch.cuda.stream(self._stream):
             out = torch.empty((self._n, self._n), dtype=tdt, device=self._tdev)
         check(lib.paos_wfo_read_device(self._handle, what, C.c_void_p(out.data_ptr())))
+        torch.cuda.current_stream(self._tdev).wait_stream(self._stream)
         return out
 
     @property

@@ -1,0 +1,142 @@
+"""GPU parity of whole surface chains (paos_b200.run) against the numpy oracle's run, per BASELINE.json config."""
+import numpy as np
+import pytest
+
+from helpers import TOL, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def both(job, dtype="complex128", noise=None, keys=None):
+    import paos_b200
+    from oracle import paos_np
+
+    args = (job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"], job["opt_chain"])
+    got = paos_b200.run(*args, dtype=dtype, psd_noise=noise, keys=keys)
+    ref = paos_np.run(*args, noise_for=noise, unit_to_m=lambda u: u.to(type(u)("m")))
+    return got, ref
+
+
+def compare(got, ref, tol, phase=True):
+    assert sorted(got) == sorted(ref) and len(ref) > 0
+    worst = 0.0
+    for num in ref:
+        g, r = got[num], ref[num]
+        for k in ("dx", "dy", "wl", "wz", "distancetofocus", "fratio", "propagator"):
+            assert g[k] == r[k], (num, k, g[k], r[k])
+        assert np.array_equal(g["extent"], r["extent"])
+        assert np.array_equal(g["ABCDt"](), r["ABCDt"]()) and np.array_equal(g["ABCDs"](), r["ABCDs"]())
+        e = relerr(g["amplitude"], r["amplitude"])
+        worst = max(worst, e)
+        assert e <= tol, (num, "amplitude", e)
+        assert relerr(g["wfo"], r["wfo"]) <= tol, (num, "wfo")
+        if "wfe" in r:
+            assert relerr(np.ma.filled(g["wfe"], 0), np.ma.filled(r["wfe"], 0)) <= 1e-11, (num, "wfe")
+        if r["aperture"] is not None:
+            ga, ra = g["aperture"], r["aperture"]
+            assert np.array_equal(ga.positions, ra.positions) and ga.theta == ra.theta
+            for attr in ("a", "b", "w", "h"):
+                if hasattr(ra, attr):
+                    assert getattr(ga, attr) == getattr(ra, attr)
+    return worst
+
+
+@pytest.mark.parametrize("grid", [256, 1024])
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_hubble(grid, dtype):
+    from paos_b200 import configs
+
+    job = configs.hubble(grid=grid)[0]
+    got, ref = both(job, dtype)
+    compare(got, ref, TOL[dtype])
+
+
+@pytest.mark.parametrize("grid,index", [(256, 0), (512, 3), (1024, 7)])
+def test_airs_ch0_all_saved_surfaces(grid, index):
+    from paos_b200 import configs
+
+    job = configs.airs_ch0(grid=grid, n_wl=8, light_output=False)[index]
+    got, ref = both(job)
+    assert len(ref) == 12
+    compare(got, ref, TOL["complex128"])
+
+
+def test_airs_ch0_complex64():
+    from paos_b200 import configs
+
+    job = configs.airs_ch0(grid=512, n_wl=4, light_output=False)[1]
+    got, ref = both(job, "complex64")
+    compare(got, ref, TOL["complex64"])
+
+
+def test_airs_ch0_off_axis_field():
+    from paos_b200 import configs
+
+    job = dict(configs.airs_ch0(grid=256, n_wl=2, light_output=False)[1])
+    job["field"] = {"us": float(np.tan(np.deg2rad(0.01))), "ut": float(np.tan(np.deg2rad(-0.02)))}
+    got, ref = both(job)
+    compare(got, ref, TOL["complex128"])
+
+
+@pytest.mark.parametrize("realization", [0, 999])
+def test_fgs1_zernike_realization(realization):
+    from paos_b200 import configs
+
+    job = configs.fgs1_montecarlo(grid=512, realizations=[realization], light_output=False)[0]
+    got, ref = both(job)
+    assert any("wfe" in v for v in ref.values())
+    compare(got, ref, TOL["complex128"])
+
+
+def test_ta_ground_psd_injected_noise():
+    from paos_b200 import configs
+
+    jobs = configs.ta_ground_psd(grid=1024, n_wl=2, light_output=False)
+    job = jobs[-1]  # last field, last wavelength
+    noise = configs.psd_noise_from_seed(job["psd_seed"])
+    got, ref = both(job, noise=noise)
+    assert any(v.get("wfe") is not None for v in ref.values())
+    compare(got, ref, TOL["complex128"])
+
+
+def test_grid_sag_chain(tmp_path):
+    from paos_b200 import configs
+
+    job = configs.grid_sag(grid=512, wavelengths=(3.0,), light_output=False, workdir=str(tmp_path))[0]
+    got, ref = both(job)
+    compare(got, ref, TOL["complex128"])
+
+
+def test_store_keys_and_reuse():
+    import paos_b200
+    from paos_b200 import configs
+
+    job = configs.hubble(grid=256)[0]
+    args = (job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"], job["opt_chain"])
+    a = paos_b200.run(*args, keys=("amplitude",))
+    w = paos_b200.WFO(1.0, 1e-6, 256, 1)
+    b = paos_b200.run(*args, keys=("amplitude",), wfo=w)
+    c = paos_b200.run(*args, keys=("amplitude",), wfo=w)  # handle re-used for a second chain
+    for num in a:
+        assert "phase" not in a[num] and "wfo" not in a[num]
+        assert np.array_equal(a[num]["amplitude"], b[num]["amplitude"])
+        assert np.array_equal(a[num]["amplitude"], c[num]["amplitude"])
+
+
+def test_sweep_matches_run():
+    import paos_b200
+    from paos_b200 import configs
+    from paos_b200.sweep import Sweep
+
+    jobs = configs.airs_ch0(grid=256, n_wl=5)
+    sw = Sweep(256, slots=2, what="amplitude")
+    host = sw.empty_stack(len(jobs), host=True)
+    out, meta = sw.run(jobs, host_out=host)
+    assert np.array_equal(out.cpu().numpy(), host.numpy())
+    for k, job in enumerate(jobs):
+        ref = paos_b200.run(job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"], job["opt_chain"])
+        last = ref[max(ref)]
+        assert np.array_equal(last["amplitude"], host[k].numpy())
+        assert meta[k]["dx"] == last["dx"] and meta[k]["propagator"] == last["propagator"]
+    st = sw.stats()
+    assert st["pass_launches"] > 0 and st["fft2_recorded"] >= 35 * len(jobs)

@@ -231,7 +231,7 @@ def test_reads_after_chain_do_not_disturb_state():
     ph = p.d.phase
     a2 = p.d.amplitude
     assert np.array_equal(a1, a2)
-    lit = p.o.amplitude > 0  # the phase of an exactly dark pixel is the sign of a zero: not compared
+    lit = p.o.amplitude > 1e-9  # dark pixels and edge slivers ~1e-15 have no meaningful phase
     dphi = np.angle(np.exp(1j * (ph - p.o.phase)))
     assert np.max(np.abs(dphi[lit])) <= 1e-9
     assert relerr(p.d.psf, p.o.amplitude**2) <= 1e-12
