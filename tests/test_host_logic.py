@@ -1,0 +1,126 @@
+"""CPU tests of the host-side logic: paraxial scalars, job builders, sharding, and the N > 1 gather on gloo."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abcd_matches_oracle():
+    import paos_b200
+    from oracle import paos_np
+
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        t, c, n1, n2, M = rng.uniform(0.1, 3), rng.uniform(-2, 2), rng.choice([1.0, -1.0, 1.5]), rng.choice([1.0, -1.0, 1.43]), rng.uniform(0.5, 2)
+        a, b = paos_b200.ABCD(t, c, n1, n2, M), paos_np.ABCD(t, c, n1, n2, M)
+        assert np.array_equal(a(), b())
+        for p in ("thickness", "M", "n1n2", "power", "f_eff", "cin", "cout"):
+            assert getattr(a, p) == getattr(b, p)
+        prod_a, prod_b = a * paos_b200.ABCD(0.3, 0.1), b * paos_np.ABCD(0.3, 0.1)
+        assert np.array_equal(prod_a(), prod_b()) and prod_a.cout == prod_b.cout
+    with pytest.raises(ValueError):
+        paos_b200.ABCD(n1=0.0)
+
+
+def test_coordinate_break_matches_oracle():
+    import paos_b200
+    from oracle import paos_np
+
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        vt, vs = rng.normal(size=2) * 0.01, rng.normal(size=2) * 0.01
+        args = (rng.normal() * 0.01, rng.normal() * 0.01, rng.normal() * 3, rng.normal() * 3, 0.0)
+        a = paos_b200.coordinate_break(vt, vs, *args)
+        b = paos_np.coordinate_break(vt, vs, *args)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    a = paos_b200.coordinate_break(np.array([0.0, 0.1]), np.array([0.0, 0.0]), np.nan, np.nan, np.nan, 2.0, 0.0)
+    b = paos_np.coordinate_break(np.array([0.0, 0.1]), np.array([0.0, 0.0]), np.nan, np.nan, np.nan, 2.0, 0.0)
+    assert np.array_equal(a[0], b[0])
+    with pytest.raises(ValueError):
+        paos_b200.coordinate_break(np.zeros(2), np.zeros(2), 0, 0, 0, 0, 0, order=1)
+
+
+def test_config_builders():
+    from paos_b200 import configs
+
+    jobs = configs.airs_ch0(grid=2048, n_wl=256)
+    assert len(jobs) == 256 and jobs[0]["gridsize"] == 2048
+    assert abs(jobs[0]["wavelength"] - 1.95e-6) < 1e-18 and abs(jobs[-1]["wavelength"] - 3.9e-6) < 1e-18
+    saved = [it["name"] for it in jobs[0]["opt_chain"].values() if it["save"]]
+    assert saved == ["IMAGE_PLANE"]
+    assert jobs[3]["opt_chain"] is not jobs[4]["opt_chain"]
+    h = configs.hubble()[0]
+    assert h["gridsize"] == 1024 and h["zoom"] == 4 and abs(h["wavelength"] - 1e-6) < 1e-20
+    f = configs.fgs1_montecarlo(grid=512, realizations=[0, 999])
+    z0, z1 = f[0]["opt_chain"][13]["Z"], f[1]["opt_chain"][13]["Z"]
+    assert len(z0) == 36 and np.all(z0[:3] == 0) and not np.array_equal(z0, z1)
+    t = configs.ta_ground_psd(grid=1024, n_wl=4)
+    assert len(t) == 36 and len({j["psd_seed"] for j in t}) == 36
+    assert any(it["type"] == "PSD" for it in t[0]["opt_chain"].values())
+    n1, n2 = configs.psd_noise_from_seed(5)(0, (4, 4))
+    rs = np.random.RandomState(5)
+    assert np.array_equal(n1, rs.randn(4, 4)) and np.array_equal(n2, rs.randn(4, 4))
+
+
+def test_grid_sag_config_is_on_grid(tmp_path):
+    from paos_b200 import configs
+
+    job = configs.grid_sag(grid=256, wavelengths=(0.55, 3.0), workdir=str(tmp_path))[1]
+    sag = [it for it in job["opt_chain"].values() if it["type"] == "Grid Sag"][0]
+    d = job["pupil_diameter"] * job["zoom"] / 256
+    assert sag["nx"] == 256 and sag["delx"] == d and sag["grid_sag"].shape == (256, 256)
+    assert np.max(np.abs(sag["grid_sag"])) <= 30e-9 + 1e-20
+
+
+def test_partition_is_contiguous_and_balanced():
+    from paos_b200 import configs
+    from paos_b200.sweep import job_cost, partition
+
+    jobs = configs.airs_ch0(grid=64, n_wl=37)
+    for world in (1, 2, 3, 8):
+        blocks = partition(jobs, world)
+        assert blocks[0][0] == 0 and blocks[-1][1] == len(jobs)
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        sizes = [b - a for a, b in blocks]
+        assert max(sizes) - min(sizes) <= 2
+    assert job_cost(jobs[0]) >= 10
+    assert partition(jobs[:2], 4) == [(0, 0), (0, 1), (1, 1), (1, 2)] or sum(b - a for a, b in partition(jobs[:2], 4)) == 2
+
+
+def _gloo_worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    from paos_b200.sweep import gather_stack, partition
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        jobs = [{"opt_chain": {}} for _ in range(5)]  # 5 jobs over 2 ranks: ragged blocks (3 + 2 or 2 + 3)
+        blocks = partition(jobs, world)
+        lo, hi = blocks[rank]
+        counts = [b - a for a, b in blocks]
+        local = torch.stack([torch.full((4, 4), float(k), dtype=torch.float64) for k in range(lo, hi)]) if hi > lo else torch.zeros((0, 4, 4), dtype=torch.float64)
+        full = gather_stack(local, counts, dst=0)
+        if rank == 0:
+            assert full.shape == (5, 4, 4)
+            assert [float(full[k, 0, 0]) for k in range(5)] == [0.0, 1.0, 2.0, 3.0, 4.0]
+            open(os.path.join(tmp, "ok"), "w").write("ok")
+        else:
+            assert full is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_stack_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+
+    port = 29600 + os.getpid() % 300
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok")

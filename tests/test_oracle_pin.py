@@ -1,0 +1,120 @@
+"""Pin the CPU oracle (oracle/paos_np.py): against the committed golden vectors, which are outputs of the
+UNMODIFIED reference (tests/golden/make_golden.py), and -- in the build container, where /root/reference exists --
+against the unmodified reference modules directly."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_cases as gc
+from oracle import paos_np, refload
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# same machine, same numpy: bit-equal in practice; the tolerance allows for a different libm / pocketfft build
+TOL = 1e-12
+
+
+def oracle_primitives():
+    def setf(w, a):
+        w._wfo = a.copy()
+
+    def psd(w, noise, **kw):
+        return w.psd(unit_to_m=1e-9, noise=noise, **kw)
+
+    return gc.primitives(paos_np.WFO, setf, lambda w: w._wfo.copy(), psd)
+
+
+def test_primitives_match_reference_golden():
+    golden = np.load(os.path.join(GOLDEN, "primitives.npz"))
+    got = oracle_primitives()
+    assert set(got) == set(golden.files)
+    worst = gc.compare_to_golden(got, golden, "", TOL)
+    assert worst <= TOL
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_chains_match_reference_golden(case, tmp_path):
+    golden = np.load(os.path.join(GOLDEN, "chains.npz"))
+    name, job, seed = gc.chain_jobs(str(tmp_path))[case]
+    noise = None
+    if seed is not None:
+        rs = np.random.RandomState(seed)
+
+        def noise(num, shape):
+            return rs.randn(*shape), rs.randn(*shape)
+
+    res = paos_np.run(job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"], job["opt_chain"],
+                      noise_for=noise, unit_to_m=lambda u: u.to(type(u)("m")))
+    got = gc.chain_summary(res)
+    assert {f"{name}/{k}" for k in got} == {f for f in golden.files if f.startswith(name + "/")}
+    gc.compare_to_golden(got, golden, name + "/", TOL)
+
+
+needs_reference = pytest.mark.skipif(not refload.reference_available(), reason="reference tree only exists in the build container")
+
+
+@needs_reference
+def test_oracle_equals_unmodified_reference_primitives():
+    ref = refload.load()
+
+    def setf(w, a):
+        w._wfo = a.copy()
+
+    def psd_ref(w, noise, **kw):
+        # the reference draws from the global numpy state: seed it so that it makes the same two draws
+        np.random.seed(11)
+        return w.psd(units=ref.units.nm, **kw)
+
+    a = gc.primitives(ref.WFO, setf, lambda w: w._wfo.copy(), psd_ref)
+    b = oracle_primitives()
+    for k in a:
+        if a[k].dtype.kind in "US":
+            assert str(a[k]) == str(b[k])
+        else:
+            assert np.array_equal(a[k], b[k]), k  # same numpy, same operation order: bit-identical
+
+
+@needs_reference
+@pytest.mark.parametrize("ordering", ["ansi", "standard", "noll", "fringe"])
+def test_zernike_index_tables_equal_reference(ordering):
+    from paos_b200 import zernike as zk
+
+    ref = refload.load()
+    m, n = zk.j2mn(66, ordering)
+    mr, nr = ref.Zernike.j2mn(66, ordering)
+    assert np.array_equal(m, mr) and np.array_equal(n, nr)
+    assert np.array_equal(zk.mn2j(m, n, ordering), ref.Zernike.mn2j(mr, nr, ordering))
+    mo, no = paos_np.j2mn(66, ordering)
+    assert np.array_equal(mo, mr) and np.array_equal(no, nr)
+
+
+@needs_reference
+@pytest.mark.parametrize("name", ["Hubble_simple", "Ariel_AIRS-CH0", "Ariel_FGS-FGS1", "lens_file_TA_Ground_PSD"])
+def test_parse_config_equals_reference(name, data_dir):
+    import paos_b200
+
+    ref = refload.load()
+    path = os.path.join(data_dir, name + ".ini")
+    a, b = paos_b200.parse_config(path), ref.parse_config(path)
+    assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
+    assert len(a[3]) == len(b[3]) and all(x == y for x, y in zip(a[3], b[3]))
+    for ca, cb in zip(a[4], b[4]):
+        assert list(ca) == list(cb)
+        for k in ca:
+            sa, sb = ca[k], cb[k]
+            assert set(sa) == set(sb)
+            for kk, va in sa.items():
+                vb = sb[kk]
+                if kk in ("ABCDt", "ABCDs"):
+                    assert np.array_equal(va(), vb()) and va.cin == vb.cin and va.cout == vb.cout
+                    for prop in ("M", "power", "thickness", "n1n2"):
+                        assert getattr(va, prop) == getattr(vb, prop) or np.isnan(getattr(va, prop))
+                elif kk == "aperture":
+                    for q in va:
+                        assert va[q] == vb[q] or (np.isnan(va[q]) and np.isnan(vb[q]))
+                elif kk == "units":
+                    assert va.name == vb.name
+                elif isinstance(va, np.ndarray):
+                    assert np.array_equal(va, vb)
+                else:
+                    assert va == vb or (isinstance(va, float) and np.isnan(va) and np.isnan(vb))
