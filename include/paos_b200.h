@@ -133,6 +133,56 @@ int paos_wfo_wts(paos_wfo *w, double wl, double dz, double dx, double dy);
 /* plain shifted transform: fftshift(fft2|ifft2(ifftshift(wfo), norm="ortho")); used by tests */
 int paos_wfo_fft2(paos_wfo *w, int inverse);
 
+/* ---- whole-chain execution (paos/core/run.py:30-228) ------------------------------------------------
+ * The reference's per-surface loop, including the Gaussian pilot-beam scalar state machine of
+ * wfo.py:304-443 and :547-572, run natively so that a sweep over many wavelengths is not limited by the
+ * Python interpreter.  One record per *non-ignored* surface after INIT, in chain order.  Every step calls
+ * the same internal operators as the per-operation entry points above, so results are those of
+ * paos_b200.run. */
+enum {
+    PAOS_SURF_GENERIC = 0,   /* Standard, Paraxial Lens, ABCD: aperture / stop / ABCD only        */
+    PAOS_SURF_COORDBREAK = 1,
+    PAOS_SURF_ZERNIKE = 2,
+    PAOS_SURF_SCREEN = 3,    /* Grid Sag already on the WFO grid (metres, 0 where masked)           */
+    PAOS_SURF_PSD = 4
+};
+typedef struct paos_surface {
+    int type;
+    int is_stop;
+    int save;              /* take a snapshot (paos_snapshot) before magnification/lens/propagation */
+    int has_aperture;
+    int ap_shape;          /* PAOS_SHAPE_ELLIPSE ("elliptical") or PAOS_SHAPE_RECT ("rectangular") */
+    int ap_obscuration;
+    int read_what;         /* PAOS_READ_* to materialise at this surface when save != 0, -1 = none */
+    int zernike_terms;
+    int zernike_origin;    /* 0 = 'x', 1 = 'y' */
+    int pad0;
+    double ap_xrad, ap_yrad, ap_xc, ap_yc;      /* as in opt_chain[..]["aperture"]; NaN centre = follow the chief ray */
+    double abcd_t[4], abcd_s[4];                /* row-major A, B, C, D of item["ABCDt"], item["ABCDs"]   */
+    double cout_t;                              /* item["ABCDt"].cout (+1 / -1)                         */
+    double xdec, ydec, xrot, yrot;              /* Coordinate Break (NaN = 0)                            */
+    double zernike_radius;                      /* NaN = use wz (run.py:131)                             */
+    double psd[8];                              /* A, B, C, fknee, fmin, fmax, SR, unit_scale            */
+    uint64_t psd_seed;
+    const int *zernike_m, *zernike_n;           /* host arrays [zernike_terms]                           */
+    const double *zernike_coef;                 /* Z[k] * norm[k]                                        */
+    const double *screen;                       /* PAOS_SURF_SCREEN: n*n host doubles                    */
+    const double *psd_noise1, *psd_noise2;      /* host arrays or NULL (device RNG from psd_seed)        */
+    void *read_dst;                             /* device destination of the read-out                    */
+} paos_surface;
+typedef struct paos_snapshot {
+    int surface;           /* index into the surface array */
+    char propagator[4];    /* "", "II", "IO", "OI", "OO" (of the previous propagation, wfo.py:572) */
+    double wl, z, w0, zw0, zr, dx, dy, C, fratio, wz, distancetofocus;
+    double vt[2], vs[2];   /* chief-ray vectors at the surface */
+} paos_snapshot;
+/* Resets the handle, runs the chain for one wavelength / field and fills one paos_snapshot per saved
+ * surface (at most max_snapshots; *n_snapshots receives the count) plus the final beam state in
+ * final_state (may be NULL).  Asynchronous like every other call. */
+int paos_chain_run(paos_wfo *w, double pupil_diameter, double wavelength, double zoom, double us, double ut,
+                   const paos_surface *surfaces, int n_surfaces, paos_snapshot *snapshots, int max_snapshots,
+                   int *n_snapshots, paos_snapshot *final_state);
+
 /* ---- statistics -------------------------------------------------------------------------------- */
 typedef struct paos_stats {
     uint64_t kernel_launches;   /* kernels of this library launched on the handle so far */

@@ -1,0 +1,160 @@
+"""Native chain execution: compile an ``opt_chain`` dictionary into ``paos_surface`` records and run the whole
+per-surface loop inside ``libpaos_b200.so`` (``paos_chain_run``), so that a sweep over hundreds of wavelengths is
+not limited by the Python interpreter.  The records carry exactly the numbers ``paos_b200.run`` would read from
+the dictionary (reference data contract: ``paos/core/parseConfig.py:155-394``); results are those of ``run``.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .zernike import j2mn, zernike_norms
+
+SURF_GENERIC, SURF_COORDBREAK, SURF_ZERNIKE, SURF_SCREEN, SURF_PSD = 0, 1, 2, 3, 4
+_TYPES = {"Standard": SURF_GENERIC, "Paraxial Lens": SURF_GENERIC, "ABCD": SURF_GENERIC,
+          "Coordinate Break": SURF_COORDBREAK, "Zernike": SURF_ZERNIKE, "Grid Sag": SURF_SCREEN, "PSD": SURF_PSD}
+_SHAPES = {"elliptical": _lib.SHAPE_ELLIPSE, "rectangular": _lib.SHAPE_RECT}
+
+
+class Surface(C.Structure):
+    _fields_ = [
+        ("type", C.c_int), ("is_stop", C.c_int), ("save", C.c_int), ("has_aperture", C.c_int), ("ap_shape", C.c_int),
+        ("ap_obscuration", C.c_int), ("read_what", C.c_int), ("zernike_terms", C.c_int), ("zernike_origin", C.c_int),
+        ("pad0", C.c_int),
+        ("ap_xrad", C.c_double), ("ap_yrad", C.c_double), ("ap_xc", C.c_double), ("ap_yc", C.c_double),
+        ("abcd_t", C.c_double * 4), ("abcd_s", C.c_double * 4), ("cout_t", C.c_double),
+        ("xdec", C.c_double), ("ydec", C.c_double), ("xrot", C.c_double), ("yrot", C.c_double),
+        ("zernike_radius", C.c_double), ("psd", C.c_double * 8), ("psd_seed", C.c_uint64),
+        ("zernike_m", C.POINTER(C.c_int)), ("zernike_n", C.POINTER(C.c_int)), ("zernike_coef", C.POINTER(C.c_double)),
+        ("screen", C.POINTER(C.c_double)), ("psd_noise1", C.POINTER(C.c_double)), ("psd_noise2", C.POINTER(C.c_double)),
+        ("read_dst", C.c_void_p),
+    ]
+
+
+class Snapshot(C.Structure):
+    _fields_ = [
+        ("surface", C.c_int), ("propagator", C.c_char * 4),
+        ("wl", C.c_double), ("z", C.c_double), ("w0", C.c_double), ("zw0", C.c_double), ("zr", C.c_double),
+        ("dx", C.c_double), ("dy", C.c_double), ("C", C.c_double), ("fratio", C.c_double), ("wz", C.c_double),
+        ("distancetofocus", C.c_double), ("vt", C.c_double * 2), ("vs", C.c_double * 2),
+    ]
+
+    def as_dict(self, n):
+        return dict(wz=self.wz, distancetofocus=self.distancetofocus, fratio=self.fratio, dx=self.dx, dy=self.dy, wl=self.wl,
+                    extent=(-n // 2 * self.dx, (n // 2 - 1) * self.dx, -n // 2 * self.dy, (n // 2 - 1) * self.dy),
+                    propagator=self.propagator.decode())
+
+
+class CompiledChain:
+    """``paos_surface`` array of one job plus the host arrays it points to (kept alive here)."""
+
+    def __init__(self, opt_chain, gridsize, pupil_diameter, zoom, psd_seed=0, psd_noise=None):
+        items = list(opt_chain.values())
+        self.n = int(gridsize)
+        self.count = len(items)
+        self.array = (Surface * max(self.count, 1))()
+        self.keep = []
+        self.nums = []
+        self.saved = []
+        for i, item in enumerate(items):
+            s = self.array[i]
+            kind = item["type"]
+            if kind not in _TYPES:
+                raise ValueError(f"Surface Type not recognised: {kind}")
+            s.type = _TYPES[kind]
+            s.is_stop = 1 if item["is_stop"] else 0
+            s.save = 1 if item["save"] else 0
+            s.read_what = -1
+            if s.save:
+                self.saved.append(i)
+            self.nums.append(item["num"])
+            if "aperture" in item:
+                ap = item["aperture"]
+                if ap["shape"] not in _SHAPES:
+                    raise ValueError(f"Aperture {ap['shape']} not supported by the native chain runner")
+                s.has_aperture = 1
+                s.ap_shape = _SHAPES[ap["shape"]]
+                s.ap_obscuration = 0 if ap["type"] == "aperture" else 1
+                s.ap_xrad, s.ap_yrad, s.ap_xc, s.ap_yc = float(ap["xrad"]), float(ap["yrad"]), float(ap["xc"]), float(ap["yc"])
+            t, sg = item["ABCDt"](), item["ABCDs"]()
+            s.abcd_t[:] = [float(t[0, 0]), float(t[0, 1]), float(t[1, 0]), float(t[1, 1])]
+            s.abcd_s[:] = [float(sg[0, 0]), float(sg[0, 1]), float(sg[1, 0]), float(sg[1, 1])]
+            s.cout_t = float(item["ABCDt"].cout)
+            s.zernike_radius = float("nan")
+            if s.type == SURF_COORDBREAK:
+                s.xdec, s.ydec, s.xrot, s.yrot = (float(item[k]) for k in ("xdec", "ydec", "xrot", "yrot"))
+            elif s.type == SURF_ZERNIKE:
+                if item["Zorthonorm"]:
+                    raise NotImplementedError("PolyOrthoNorm screens are not on the device path yet")
+                if item["Zorigin"] not in ("x", "y"):
+                    raise ValueError(f"Origin {item['Zorigin']} not recognised. Origin shall be either x or y")
+                index = np.asarray(item["Zindex"])
+                assert not np.any(np.diff(index) - 1), "Zernike sequence should be continuous"
+                K = len(index)
+                m, n = j2mn(K, item["Zordering"])
+                coef = np.ascontiguousarray(np.asarray(item["Z"], dtype=np.float64) * zernike_norms(m, n, item["Znormalize"]))
+                m32, n32 = np.ascontiguousarray(m, dtype=np.int32), np.ascontiguousarray(n, dtype=np.int32)
+                self.keep += [coef, m32, n32]
+                s.zernike_terms = K
+                s.zernike_origin = 0 if item["Zorigin"] == "x" else 1
+                s.zernike_m = m32.ctypes.data_as(C.POINTER(C.c_int))
+                s.zernike_n = n32.ctypes.data_as(C.POINTER(C.c_int))
+                s.zernike_coef = coef.ctypes.data_as(C.POINTER(C.c_double))
+                s.zernike_radius = float(item["Zradius"])
+            elif s.type == SURF_SCREEN:
+                screen = _on_grid_sag(item, self.n, pupil_diameter, zoom)
+                self.keep.append(screen)
+                s.screen = screen.ctypes.data_as(C.POINTER(C.c_double))
+            elif s.type == SURF_PSD:
+                from .wfo import _unit_to_m
+
+                vals = [item["A"], item["B"], item["C"], item["fknee"], item["fmin"], item["fmax"], item["SR"], _unit_to_m(item["units"])]
+                s.psd[:] = [float(v) for v in vals]
+                s.psd_seed = int(psd_seed)
+                if psd_noise is not None:
+                    n1, n2 = psd_noise(item["num"], (self.n, self.n))
+                    n1 = np.ascontiguousarray(n1, dtype=np.float64)
+                    n2 = np.ascontiguousarray(n2, dtype=np.float64)
+                    self.keep += [n1, n2]
+                    s.psd_noise1 = n1.ctypes.data_as(C.POINTER(C.c_double))
+                    s.psd_noise2 = n2.ctypes.data_as(C.POINTER(C.c_double))
+        self.snapshots = (Snapshot * max(len(self.saved), 1))()
+        self.final = Snapshot()
+        self.nsnap = C.c_int(0)
+
+    def set_readout(self, surface_index, what, dev_ptr):
+        s = self.array[surface_index]
+        s.read_what = int(what)
+        s.read_dst = dev_ptr
+
+
+def _on_grid_sag(item, n, pupil_diameter, zoom):
+    """Screen (metres, 0 where masked) of a Grid Sag surface that already sits on the WFO grid at INIT sampling;
+    the general case goes through ``WFO.grid_sag`` in the Python driver."""
+    sag = item["grid_sag"]
+    if not isinstance(sag, np.ma.MaskedArray):
+        sag = np.ma.MaskedArray(sag, mask=~np.isfinite(sag) | (sag == 0))
+    d = pupil_diameter * zoom / n
+    if not (sag.shape == (n, n) and item["xdec"] == 0 and item["ydec"] == 0 and item["delx"] == d and item["dely"] == d):
+        raise NotImplementedError("the native chain runner takes grid-sag maps that are already on the WFO grid")
+    return np.ascontiguousarray(sag.filled(0.0), dtype=np.float64)
+
+
+def compile_job(job, psd_noise=None):
+    """Compile (and cache on the job dict) the native surface records of a job."""
+    cc = job.get("_compiled")
+    if cc is None or psd_noise is not None:
+        cc = CompiledChain(job["opt_chain"], job["gridsize"], job["pupil_diameter"], job["zoom"],
+                           psd_seed=job.get("psd_seed", 0), psd_noise=psd_noise)
+        if psd_noise is None:
+            job["_compiled"] = cc
+    return cc
+
+
+def run_compiled(wfo, job, cc):
+    """Enqueue one compiled chain on ``wfo`` (asynchronous); returns the list of snapshot dicts of saved surfaces."""
+    _lib.check(_lib.lib.paos_chain_run(
+        wfo._handle, float(job["pupil_diameter"]), float(job["wavelength"]), float(job["zoom"]), float(job["field"]["us"]),
+        float(job["field"]["ut"]), cc.array, cc.count, cc.snapshots, len(cc.saved), C.byref(cc.nsnap), C.byref(cc.final)))
+    wfo._sync_scalars(cc.final)
+    return [cc.snapshots[k].as_dict(cc.n) for k in range(min(cc.nsnap.value, len(cc.saved)))]

@@ -41,7 +41,7 @@ struct PassParams {
     const void* ctab_in;       // cross-axis complex table, one value per line, applied at position 0 (null = none)
     const void* ctab_out;      // same, applied after the last position
     unsigned genmask;          // bit p set: some general factor sits at position p
-    int pad0;
+    unsigned sgnmask;          // bit p set: position p carries the sign (-1)^index (no table)
     int readout;               // 0: store the complex field; PAOS_READ_* (1..3): store a real read-out into dst_real instead
     int pad;
     void* dst_real;

@@ -233,9 +233,11 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
         const C<R>* tab = reinterpret_cast<const C<R>*>(P.tab[pos]);
         if (tab) {
 #pragma unroll
-            for (int j = 0; j < E; ++j) v[j] = v[j] * ldc_ro(tab + t + j * T);
+            for (int j = 0; j < E; ++j) v[j] = v[j] * ldc_once(tab + t + j * T);
         } else {
-            const R s = (R)P.scl[pos];
+            // real scale, with the (-1)^index sign of an fftshift when flagged (index parity = t parity: T is even)
+            R s = (R)P.scl[pos];
+            if ((P.sgnmask >> pos & 1) && (t & 1)) s = -s;
             if (s != (R)1) {
 #pragma unroll
                 for (int j = 0; j < E; ++j) v[j] = v[j] * s;

@@ -146,7 +146,7 @@ struct PosAcc {  // what accumulates at one position of a pass
     bool sign = false;
     double scale = 1.0;
     TableTerm terms[TERM_MAX];
-    bool trivial() const { return nterms == 0 && !sign; }
+    bool trivial() const { return nterms == 0; }  // a real scale and/or the (-1)^k sign: no table needed
 };
 
 struct TimedLaunch {
@@ -381,8 +381,10 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
         for (int p = 0; p <= P.nfft; ++p) {
             P.scl[p] = 1.0;
             P.tab[p] = nullptr;
-            if (acc[p].trivial()) P.scl[p] = acc[p].scale;
-            else {
+            if (acc[p].trivial()) {
+                P.scl[p] = acc[p].scale;
+                if (acc[p].sign) P.sgnmask |= 1u << p;
+            } else {
                 int rc = spec_from_acc(w, acc[p], plan, &P.tab[p]);
                 if (rc) return rc;
             }
@@ -1060,3 +1062,223 @@ int paos_wfo_timing_detail(paos_wfo* w, int col, int nfft, double* ms, uint64_t*
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// whole-chain execution: the per-surface loop of paos/core/run.py:30-228 with the pilot-beam scalar state
+// machine of paos/classes/wfo.py:280-443, :547-572 in C++ doubles (same expressions, same order)
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct Beam {
+    double wl, z, w0, zw0, zr, rf, dx, dy, C, fratio;
+    int n;
+    char prop[4];
+};
+
+inline double sq(double x) { return x * x; }
+inline double beam_wz(const Beam& b) { return b.w0 * std::sqrt(1.0 + sq((b.z - b.zw0) / b.zr)); }
+inline char beam_io(const Beam& b, double z) { return std::fabs(z - b.zw0) < b.rf * b.zr ? 'I' : 'O'; }
+
+int beam_lens(paos_wfo* w, Beam& b, double fl) {
+    const double wz = beam_wz(b);
+    double delta_z = b.z - b.zw0;
+    const char before = beam_io(b, b.z);
+    const double gCobj = delta_z / (sq(delta_z) + sq(b.zr));
+    const double gCima = gCobj - 1.0 / fl;
+    b.w0 = wz / std::sqrt(1.0 + sq(M_PI * sq(wz) * gCima / b.wl));
+    b.zw0 = -gCima / (sq(gCima) + sq(b.wl / (M_PI * sq(wz)))) + b.z;
+    b.zr = M_PI * sq(b.w0) / b.wl;
+    const char after = beam_io(b, b.z);
+    const double Cobj = (before == 'I' || b.C == 0.0) ? 0.0 : 1.0 / delta_z;
+    delta_z = b.z - b.zw0;
+    const double Cima = after == 'I' ? 0.0 : 1.0 / delta_z;
+    b.C = Cima;
+    double lens_phase = 1.0 / fl;
+    if (before == 'O') lens_phase = lens_phase - Cobj;
+    if (after == 'O') lens_phase = lens_phase + Cima;
+    b.fratio = std::fabs(delta_z) / (2 * wz);
+    return paos_wfo_quadphase(w, -2.0 * M_PI, 0.5 * lens_phase / b.wl, b.dx, b.dy);
+}
+
+int beam_magnify(Beam& b, double My, double Mx) {
+    if (!(Mx > 0.0) || !(My > 0.0)) return fail(PAOS_ERR_ARG, "Negative magnification not implemented yet.");
+    b.dx *= Mx;
+    b.dy *= My;
+    if (std::fabs(Mx - 1.0) < 1.0e-8) return PAOS_OK;
+    double delta_z = b.z - b.zw0;
+    double wz = beam_wz(b);
+    delta_z *= sq(Mx);
+    wz *= Mx;
+    b.w0 *= Mx;
+    b.zr *= sq(Mx);
+    b.zw0 = b.z - delta_z;
+    b.fratio = std::fabs(delta_z) / (2 * wz);
+    return PAOS_OK;
+}
+
+void beam_medium(Beam& b, double n1n2) {
+    double delta_z = b.z - b.zw0;
+    delta_z /= n1n2;
+    b.zr /= n1n2;
+    b.wl *= n1n2;
+    b.zw0 = b.z - delta_z;
+    b.fratio /= n1n2;
+}
+
+int beam_ptp(paos_wfo* w, Beam& b, double dz) {
+    if (std::fabs(dz) < 0.001 * b.wl) return PAOS_OK;
+    if (b.C != 0) return fail(PAOS_ERR_STATE, "PTP wavefront should be planar");
+    int rc = paos_wfo_ptp(w, b.wl, dz, b.dx, b.dy);
+    b.z = b.z + dz;
+    return rc;
+}
+int beam_stw(paos_wfo* w, Beam& b, double dz) {
+    if (std::fabs(dz) < 0.001 * b.wl) return PAOS_OK;
+    if (b.C == 0.0) return fail(PAOS_ERR_STATE, "STW wavefront should not be planar");
+    int rc = paos_wfo_stw(w, b.wl, dz, b.dx, b.dy);
+    const double fx1 = 1 * (1.0 / (b.n * b.dx)), fy1 = 1 * (1.0 / (b.n * b.dy));
+    b.z = b.z + dz;
+    b.C = 0.0;
+    b.dx = (fx1 - 0.0) * b.wl * std::fabs(dz);
+    b.dy = (fy1 - 0.0) * b.wl * std::fabs(dz);
+    return rc;
+}
+int beam_wts(paos_wfo* w, Beam& b, double dz) {
+    if (std::fabs(dz) < 0.001 * b.wl) return PAOS_OK;
+    if (b.C != 0.0) return fail(PAOS_ERR_STATE, "WTS wavefront should be planar");
+    int rc = paos_wfo_wts(w, b.wl, dz, b.dx, b.dy);
+    b.z = b.z + dz;
+    b.C = 1 / (b.z - b.zw0);
+    b.dx = b.wl * std::fabs(dz) / (b.n * b.dx);
+    b.dy = b.wl * std::fabs(dz) / (b.n * b.dy);
+    return rc;
+}
+int beam_propagate(paos_wfo* w, Beam& b, double dz) {
+    const double z1 = b.z, z2 = b.z + dz;
+    const char p0 = beam_io(b, b.z), p1 = beam_io(b, z2);
+    int rc = PAOS_OK;
+    if (p0 == 'O') rc = beam_stw(w, b, b.zw0 - z1);
+    else rc = (p1 == 'I') ? beam_ptp(w, b, dz) : beam_ptp(w, b, b.zw0 - z1);
+    if (rc) return rc;
+    if (p1 == 'O') rc = beam_wts(w, b, z2 - b.zw0);
+    else if (p0 == 'O') rc = beam_ptp(w, b, z2 - b.zw0);
+    b.prop[0] = p0;
+    b.prop[1] = p1;
+    b.prop[2] = 0;
+    return rc;
+}
+
+// paos/core/coordinateBreak.py:7-72 : decenter, rotate into the new frame (scipy 'xyz' = rotations about the
+// fixed x, then y, then z axes: R = Rz*Ry*Rx; the new frame sees R^T v), re-intersect with z = 0
+void chain_coordinate_break(double vt[2], double vs[2], double xdec, double ydec, double xrot, double yrot, double zrot) {
+    auto fin = [](double v) { return std::isfinite(v) ? v : 0.0; };
+    xdec = fin(xdec); ydec = fin(ydec);
+    const double a = fin(xrot) * M_PI / 180.0, bb = fin(yrot) * M_PI / 180.0, c = fin(zrot) * M_PI / 180.0;
+    const double ca = std::cos(a), sa = std::sin(a), cb = std::cos(bb), sb = std::sin(bb), cc = std::cos(c), sc = std::sin(c);
+    // R = Rz(c) * Ry(b) * Rx(a)
+    const double R[3][3] = {{cc * cb, cc * sb * sa - sc * ca, cc * sb * ca + sc * sa},
+                            {sc * cb, sc * sb * sa + cc * ca, sc * sb * ca - cc * sa},
+                            {-sb, cb * sa, cb * ca}};
+    auto applyT = [&](const double v[3], double o[3]) {
+        for (int i = 0; i < 3; ++i) o[i] = R[0][i] * v[0] + R[1][i] * v[1] + R[2][i] * v[2];
+    };
+    const double r0[3] = {vs[0] - xdec, vt[0] - ydec, 0.0}, n0[3] = {vs[1], vt[1], 1.0};
+    double n1[3], r1l[3];
+    applyT(n0, n1);
+    const double nz = n1[2];
+    for (double& v : n1) v /= nz;
+    applyT(r0, r1l);
+    double r1[3];
+    for (int i = 0; i < 3; ++i) r1[i] = r1l[i] - n1[i] * r1l[2] / n1[2];
+    vt[0] = r1[1];
+    vt[1] = n1[1];
+    vs[0] = r1[0];
+    vs[1] = n1[0];
+}
+
+void fill_snapshot(paos_snapshot& s, int index, const Beam& b, const double vt[2], const double vs[2]) {
+    s.surface = index;
+    std::memcpy(s.propagator, b.prop, 4);
+    s.wl = b.wl; s.z = b.z; s.w0 = b.w0; s.zw0 = b.zw0; s.zr = b.zr; s.dx = b.dx; s.dy = b.dy; s.C = b.C; s.fratio = b.fratio;
+    s.wz = beam_wz(b);
+    s.distancetofocus = b.zw0 - b.z;
+    s.vt[0] = vt[0]; s.vt[1] = vt[1]; s.vs[0] = vs[0]; s.vs[1] = vs[1];
+}
+
+}  // namespace
+
+extern "C" int paos_chain_run(paos_wfo* w, double pupil_diameter, double wavelength, double zoom, double us, double ut,
+                              const paos_surface* surfaces, int n_surfaces, paos_snapshot* snapshots, int max_snapshots,
+                              int* n_snapshots, paos_snapshot* final_state) {
+    if (!w || (!surfaces && n_surfaces > 0)) return fail(PAOS_ERR_ARG, "null argument");
+    if (!(zoom > 0) || !(pupil_diameter > 0) || !(wavelength > 0)) return fail(PAOS_ERR_ARG, "zoom, beam diameter and wavelength must be positive");
+    int rc = paos_wfo_reset(w);
+    if (rc) return rc;
+    Beam b{};
+    b.n = w->n;
+    b.wl = wavelength;
+    b.z = 0.0;
+    b.w0 = pupil_diameter / 2.0;
+    b.zw0 = 0.0;
+    b.zr = M_PI * sq(b.w0) / wavelength;
+    b.rf = 2.0;
+    b.dx = pupil_diameter * zoom / b.n;
+    b.dy = pupil_diameter * zoom / b.n;
+    b.C = 0.0;
+    b.fratio = INFINITY;
+    b.prop[0] = 0;
+    double vt[2] = {0.0, ut}, vs[2] = {0.0, us};
+    int nsnap = 0;
+    for (int i = 0; i < n_surfaces; ++i) {
+        const paos_surface& s = surfaces[i];
+        if (s.type == PAOS_SURF_COORDBREAK) chain_coordinate_break(vt, vs, s.xdec, s.ydec, s.xrot, s.yrot, 0.0);
+        if (s.has_aperture) {
+            const double xc = std::isfinite(s.ap_xc) ? s.ap_xc : vs[0], yc = std::isfinite(s.ap_yc) ? s.ap_yc : vt[0];
+            const double xrad = s.ap_xrad * std::sqrt(1 / (sq(vs[1]) + 1)), yrad = s.ap_yrad * std::sqrt(1 / (sq(vt[1]) + 1));
+            if (std::isfinite(xrad) && std::isfinite(yrad)) {
+                const double ixc = (xc - vs[0]) / b.dx + b.n / 2.0, iyc = (yc - vt[0]) / b.dy + b.n / 2.0;
+                rc = paos_wfo_aperture(w, s.ap_shape, ixc, iyc, xrad / b.dx, yrad / b.dy, 0.0, s.ap_obscuration);
+                if (rc) return rc;
+            }
+        }
+        if (s.is_stop && (rc = paos_wfo_make_stop(w))) return rc;
+        if (s.type == PAOS_SURF_ZERNIKE) {
+            const double radius = std::isfinite(s.zernike_radius) ? s.zernike_radius : beam_wz(b);
+            rc = paos_wfo_zernike(w, s.zernike_terms, s.zernike_m, s.zernike_n, s.zernike_coef, radius, b.dx, b.dy, 0.0,
+                                  s.zernike_origin, b.wl, nullptr);
+            if (rc) return rc;
+        } else if (s.type == PAOS_SURF_SCREEN) {
+            if ((rc = paos_wfo_phase_screen(w, s.screen, b.wl))) return rc;
+        } else if (s.type == PAOS_SURF_PSD) {
+            const double f_nyq = 0.5 * std::sqrt(1.0 / sq(b.dx) + 1.0 / sq(b.dy));
+            if (!(s.psd[5] <= f_nyq)) return fail(PAOS_ERR_ARG, "fmax must be less than or equal to f_Nyq (%g)", f_nyq);
+            rc = paos_wfo_psd(w, s.psd[0], s.psd[1], s.psd[2], s.psd[3], s.psd[4], s.psd[5], s.psd[6], s.psd[7], b.dx, b.dy, b.wl,
+                              s.psd_noise1, s.psd_noise2, s.psd_seed, nullptr);
+            if (rc) return rc;
+        }
+        if (s.save) {
+            if (s.read_what >= 0 && s.read_dst && (rc = paos_wfo_read_device(w, s.read_what, s.read_dst))) return rc;
+            if (snapshots && nsnap < max_snapshots) fill_snapshot(snapshots[nsnap], i, b, vt, vs);
+            ++nsnap;
+        }
+        const double At = s.abcd_t[0], Bt = s.abcd_t[1], Ct = s.abcd_t[2], Dt = s.abcd_t[3];
+        const double As = s.abcd_s[0], Bs = s.abcd_s[1], Cs = s.abcd_s[2], Ds = s.abcd_s[3];
+        const double Mt = (At * Dt - Bt * Ct) / Dt, Ms = (As * Ds - Bs * Cs) / Ds;
+        const double power = -Ct / Mt;
+        const double fl = power == 0 ? INFINITY : s.cout_t / power;
+        const double T = s.cout_t * (Bt / Dt);
+        const double n1n2 = Dt * Mt;
+        if (Mt != 1.0 || Ms != 1.0) {
+            if ((rc = beam_magnify(b, Mt, Ms))) return rc;
+        }
+        if (std::fabs(n1n2) != 1.0) beam_medium(b, n1n2);
+        if (std::isfinite(fl) && (rc = beam_lens(w, b, fl))) return rc;
+        if (std::isfinite(T) && std::fabs(T) > 1e-10 && (rc = beam_propagate(w, b, T))) return rc;
+        const double vt0 = At * vt[0] + Bt * vt[1], vt1 = Ct * vt[0] + Dt * vt[1];
+        const double vs0 = As * vs[0] + Bs * vs[1], vs1 = Cs * vs[0] + Ds * vs[1];
+        vt[0] = vt0; vt[1] = vt1; vs[0] = vs0; vs[1] = vs1;
+    }
+    if (n_snapshots) *n_snapshots = nsnap;
+    if (final_state) fill_snapshot(*final_state, n_surfaces, b, vt, vs);
+    return PAOS_OK;
+}

@@ -65,7 +65,7 @@ class Sweep:
             return torch.empty((count, self.n, self.n), dtype=self.rdtype, pin_memory=True)
         return torch.empty((count, self.n, self.n), dtype=self.rdtype, device=self.tdev)
 
-    def run(self, jobs, out=None, host_out=None, psd_noise=None):
+    def run(self, jobs, out=None, host_out=None, psd_noise=None, native=True):
         """Propagate ``jobs``; the last saved surface of job k is read out (``what``) into ``out[k]``.
 
         ``out``: device stack (allocated when None).  ``host_out``: optional pinned host stack that also receives
@@ -80,10 +80,28 @@ class Sweep:
         code = READS[self.what]
         meta = []
         nslots = len(self.wfos)
+        from . import chain as chain_mod
+
         for k, job in enumerate(jobs):
             s = k % nslots
             wfo, stream = self.wfos[s], self.streams[s]
             dst = out[k]
+            if native:
+                # whole chain planned and enqueued inside the library (paos_chain_run)
+                cc = chain_mod.compile_job(job, psd_noise(job) if psd_noise is not None else None)
+                if not cc.saved:
+                    raise ValueError(f"job {job.get('tag', k)} saves no surface")
+                for idx in cc.saved:
+                    cc.set_readout(idx, -1, None)
+                cc.set_readout(cc.saved[-1], code, dst.data_ptr())
+                snaps = chain_mod.run_compiled(wfo, job, cc)
+                last = snaps[-1]
+                last["tag"] = job.get("tag", str(k))
+                meta.append(last)
+                if host_out is not None:
+                    with torch.cuda.stream(stream):
+                        host_out[k].copy_(dst, non_blocking=True)
+                continue
 
             def snapshot(w, item, dst=dst):
                 _lib.check(_lib.lib.paos_wfo_read_device(w._handle, code, C.c_void_p(dst.data_ptr())))

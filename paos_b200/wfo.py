@@ -85,6 +85,12 @@ class WFO:
         self._zoom = zoom
         self._propagator = ""
 
+    def _sync_scalars(self, st):
+        """Adopt the pilot-beam state reported by the native chain runner (``paos_snapshot``)."""
+        self._wl, self._z, self._w0, self._zw0, self._zr = st.wl, st.z, st.w0, st.zw0, st.zr
+        self._dx, self._dy, self._C, self._fratio = st.dx, st.dy, st.C, st.fratio
+        self._propagator = st.propagator.decode()
+
     def reset(self, beam_diameter, wl, zoom):
         """Start a new chain on the same device buffer (extension: avoids re-allocating per propagation)."""
         self._set_beam(beam_diameter, wl, self._n, zoom)
