@@ -15,7 +15,7 @@ SOURCES = ["runtime.cu", "aux_kernels.cu", "pass_c128.cu", "pass_c64.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v",
-]
+] + (os.environ.get("PAOS_NVCC_EXTRA", "").split())
 
 
 def _newest_dep():

@@ -146,6 +146,9 @@ template <typename R> __device__ __forceinline__ void dft16(C<R>* v) {
 }
 
 template <int RADIX, typename R> __device__ __forceinline__ void dft(C<R>* v) {
+#ifdef PAOS_EXP_NO_DP
+    return;
+#endif
     if constexpr (RADIX == 2) dft2(v[0], v[1]);
     else if constexpr (RADIX == 4) dft4(v[0], v[1], v[2], v[3]);
     else if constexpr (RADIX == 8) dft8(v);
@@ -183,32 +186,58 @@ __device__ __forceinline__ void line_fft_fwd(C<R>* v, int t, C<R>* sm, const C<R
                                              const C<R>* __restrict__ tw2, SYNC sync) {
     constexpr int E = G::E, T = G::T, R2 = G::R2, TP = G::TP;
     // stage 1: radix-E over j, twiddle W_N^(k1*t)
+#ifndef PAOS_TABLE_TWIDDLES
+    // load only the power-of-two twiddles (issued before the butterfly so their latency hides behind it) and
+    // form the others by one or two products (error <= ~3 ulp), instead of E-1 dependent table loads
+    C<R> wp[E];
+#pragma unroll
+    for (int b = 1; b < E; b <<= 1) wp[b] = ldc_ro(tw1 + (b - 1) * T + t);
+    dft<E>(v);
+#pragma unroll
+    for (int k1 = 1; k1 < E; ++k1) {
+        const int hb = (k1 >= 8) ? 8 : (k1 >= 4) ? 4 : (k1 >= 2) ? 2 : 1;  // highest set bit
+        if (k1 != hb) wp[k1] = wp[hb] * wp[k1 - hb];
+#ifndef PAOS_EXP_NO_DP
+        v[k1] = v[k1] * wp[k1];
+#endif
+    }
+#else
     dft<E>(v);
 #pragma unroll
     for (int k1 = 1; k1 < E; ++k1) v[k1] = v[k1] * ldc_ro(tw1 + (k1 - 1) * T + t);
+#endif
+#ifndef PAOS_EXP_NO_SMEM
     sync();  // previous readers of the buffer are done
 #pragma unroll
     for (int k1 = 0; k1 < E; ++k1) stc(sm + k1 * TP + t, v[k1]);
     sync();
+#endif
     if constexpr (R2 == 1) {
         // two-stage: thread p = k1 gathers A[p][n3]
 #pragma unroll
+#ifndef PAOS_EXP_NO_SMEM
         for (int n3 = 0; n3 < E; ++n3) v[n3] = ldc(sm + t * TP + n3);
+#endif
     } else {
         const int n3 = t % E, q = t / E;
         constexpr int NB = E / R2;  // butterflies per thread
+#ifndef PAOS_EXP_NO_SMEM
 #pragma unroll
         for (int c = 0; c < NB; ++c)
 #pragma unroll
             for (int n2 = 0; n2 < R2; ++n2) v[c * R2 + n2] = ldc(sm + (q + R2 * c) * TP + n2 * E + n3);
+#endif
 #pragma unroll
         for (int c = 0; c < NB; ++c) dft<R2>(v + c * R2);
 #pragma unroll
         for (int k2 = 1; k2 < R2; ++k2) {
             C<R> w = ldc_ro(tw2 + (k2 - 1) * E + n3);
 #pragma unroll
+#ifndef PAOS_EXP_NO_DP
             for (int c = 0; c < NB; ++c) v[c * R2 + k2] = v[c * R2 + k2] * w;
+#endif
         }
+#ifndef PAOS_EXP_NO_SMEM
         sync();
 #pragma unroll
         for (int c = 0; c < NB; ++c)
@@ -217,6 +246,7 @@ __device__ __forceinline__ void line_fft_fwd(C<R>* v, int t, C<R>* sm, const C<R
         sync();
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = ldc(sm + m * TP + t);
+#endif
     }
     // stage 3: radix-E over n3 -> X[t + k3*T]
     dft<E>(v);

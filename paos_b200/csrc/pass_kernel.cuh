@@ -187,23 +187,31 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
                 const GenOp& g = P.gen[gi];
                 if (g.pos != pos) continue;
                 if (g.kind == GEN_ELLIPSE) {
-                    // interior / exterior pixels are classified inline (p5, p6 = squared radii of the bands in
-                    // which a pixel is certainly inside / outside); only edge pixels take the exact routine
-                    const double inside = g.flag ? 0.0 : 1.0, outside = g.flag ? 1.0 : 0.0;
+                    // Interior / exterior pixels are classified in FP32 (its pipe is idle next to the FP64 butterflies):
+                    // p5, p6 = squared radii, in the frame where the ellipse is the unit circle, inside / outside which
+                    // a whole pixel is certainly inside / outside; the 1e-5 margins cover the float rounding.  Only
+                    // pixels in the thin band between them take the exact (double) routine.
+                    const float cxf = (float)g.p0, cyf = (float)g.p1, sxf = (float)g.p2, syf = (float)g.p3;
+                    const float in5 = (float)g.p5 - 1e-5f, out6 = (float)g.p6 + 1e-5f;
+                    const float a0 = COL ? ((float)t - cyf) * syf : ((float)t - cxf) * sxf;
+                    const float da = COL ? (float)T * syf : (float)T * sxf;
+                    const float bq = COL ? ((float)line - cxf) * sxf : ((float)line - cyf) * syf;
+                    const float b2 = bq * bq;
+                    const bool obsc = g.flag != 0;
 #pragma unroll
                     for (int j = 0; j < E; ++j) {
-                        const int idx = t + j * T;
-                        const int ix = COL ? line : idx, iy = COL ? idx : line;
-                        const double u = ((double)ix - g.p0) * g.p2, w2 = ((double)iy - g.p1) * g.p3;
-                        const double r2 = u * u + w2 * w2;
-                        double m;
-                        if (r2 <= g.p5) m = inside;
-                        else if (r2 >= g.p6) m = outside;
-                        else {
-                            double fi;
-                            gen_factor_slow(g, ix, iy, N, m, fi);
+                        const float aq = a0 + (float)j * da;
+                        const float r2 = aq * aq + b2;
+                        if (r2 <= in5) {
+                            if (obsc) v[j] = C<R>((R)0, (R)0);
+                        } else if (r2 >= out6) {
+                            if (!obsc) v[j] = C<R>((R)0, (R)0);
+                        } else {
+                            const int idx = t + j * T;
+                            double m, fi;
+                            gen_factor_slow(g, COL ? line : idx, COL ? idx : line, N, m, fi);
+                            v[j] = v[j] * (R)m;
                         }
-                        v[j] = v[j] * (R)m;
                     }
                 } else if (g.kind == GEN_RECT) {
 #pragma unroll
@@ -233,7 +241,7 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
         const C<R>* tab = reinterpret_cast<const C<R>*>(P.tab[pos]);
         if (tab) {
 #pragma unroll
-            for (int j = 0; j < E; ++j) v[j] = v[j] * ldc_once(tab + t + j * T);
+            for (int j = 0; j < E; ++j) v[j] = v[j] * ldc_ro(tab + t + j * T);
         } else {
             // real scale, with the (-1)^index sign of an fftshift when flagged (index parity = t parity: T is even)
             R s = (R)P.scl[pos];
@@ -248,6 +256,16 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
         if (inv) {
 #pragma unroll
             for (int j = 0; j < E; ++j) v[j] = C<R>(v[j].y, v[j].x);
+        }
+        {
+            // pull the next position's phase table into L1 while this transform runs (one 128-byte line per
+            // prefetch; the table is N complex values, shared by every line of the pass)
+            const char* nxt = reinterpret_cast<const char*>(P.tab[pos + 1]);
+            if (nxt) {
+                constexpr int LINES = N * (int)sizeof(C<R>) / 128;
+#pragma unroll
+                for (int i = t; i < LINES; i += T) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + (size_t)i * 128));
+            }
         }
         line_fft_fwd<G, R>(v, t, sm, tw1, tw2, sync);
         if (inv) {

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -406,6 +407,22 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
         pp.col = false;
         pp.P = P;
         plan.passes.push_back(pp);
+    }
+    // timing experiments only (results are wrong): drop the general factors / the phase tables from every pass
+    static const bool exp_nogen = getenv("PAOS_EXP_SKIP_GENS") != nullptr, exp_notab = getenv("PAOS_EXP_SKIP_TABLES") != nullptr;
+    for (PlannedPass& pp : plan.passes) {
+        if (exp_nogen) { pp.P.ngen = 0; pp.P.genmask = 0; }
+        if (exp_notab) for (int p2 = 0; p2 <= KMAX; ++p2) pp.P.tab[p2] = nullptr;
+    }
+    static const bool debug_plan = getenv("PAOS_DEBUG_PLAN") != nullptr;
+    if (debug_plan) {
+        for (const PlannedPass& pp : plan.passes) {
+            int ntab = 0;
+            for (int p2 = 0; p2 <= pp.P.nfft; ++p2) ntab += pp.P.tab[p2] != nullptr;
+            fprintf(stderr, "[plan] %s nfft=%d tables=%d gens=%d (", pp.col ? "col" : "row", pp.P.nfft, ntab, pp.P.ngen);
+            for (int g2 = 0; g2 < pp.P.ngen; ++g2) fprintf(stderr, "%d@%d ", pp.P.gen[g2].kind, pp.P.gen[g2].pos);
+            fprintf(stderr, ") ctab=%d%d src=%d\n", pp.P.ctab_in != nullptr, pp.P.ctab_out != nullptr, pp.P.src != nullptr);
+        }
     }
     if (readout && !plan.passes.empty()) {
         plan.passes.back().P.readout = readout;
