@@ -40,6 +40,36 @@ def partition(jobs, world_size):
     return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
 
 
+def bind_to_gpu_numa(device):
+    """Pin the calling process (and therefore the pinned host buffers it allocates next) to the CPUs of the NUMA
+    node the GPU hangs off, so that device-to-host copies do not cross the socket interconnect.  Best effort:
+    returns the NUMA node or None when the topology cannot be read."""
+    import os
+
+    try:
+        import torch
+
+        prop = torch.cuda.get_device_properties(device)
+        bus = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 class Sweep:
     """Persistent executor for jobs of one grid size on one GPU."""
 
@@ -65,12 +95,14 @@ class Sweep:
             return torch.empty((count, self.n, self.n), dtype=self.rdtype, pin_memory=True)
         return torch.empty((count, self.n, self.n), dtype=self.rdtype, device=self.tdev)
 
-    def run(self, jobs, out=None, host_out=None, psd_noise=None, native=True):
+    def run(self, jobs, out=None, host_out=None, psd_noise=None, native=True, cache_compiled=True):
         """Propagate ``jobs``; the last saved surface of job k is read out (``what``) into ``out[k]``.
 
         ``out``: device stack (allocated when None).  ``host_out``: optional pinned host stack that also receives
-        every result (asynchronous device-to-host copies inside the pipeline).  Returns ``(out, meta)`` with one
-        ``meta`` dict of host scalars per job.  The call returns after all device work has completed.
+        every result (asynchronous device-to-host copies inside the pipeline; a stack shorter than ``jobs`` is used
+        as a ring).  ``native``: run each chain through ``paos_chain_run`` (C++ per-surface loop) instead of the
+        Python driver; ``cache_compiled=False`` rebuilds the native surface records of every job on every call.
+        Returns ``(out, meta)`` with one ``meta`` dict of host scalars per job, after all device work has completed.
         """
         import ctypes as C
 
@@ -88,6 +120,8 @@ class Sweep:
             dst = out[k]
             if native:
                 # whole chain planned and enqueued inside the library (paos_chain_run)
+                if not cache_compiled:
+                    job.pop("_compiled", None)
                 cc = chain_mod.compile_job(job, psd_noise(job) if psd_noise is not None else None)
                 if not cc.saved:
                     raise ValueError(f"job {job.get('tag', k)} saves no surface")
@@ -100,7 +134,7 @@ class Sweep:
                 meta.append(last)
                 if host_out is not None:
                     with torch.cuda.stream(stream):
-                        host_out[k].copy_(dst, non_blocking=True)
+                        host_out[k % host_out.shape[0]].copy_(dst, non_blocking=True)
                 continue
 
             def snapshot(w, item, dst=dst):
