@@ -15,9 +15,9 @@ cudaError_t launch_pass_c128(int n, bool col, const PassParams& P, const void* t
         //        N    E  Wrow Wcol minb
         PAOS_CASE(64, 8, 16, 16, 1, 1)
         PAOS_CASE(128, 8, 8, 8, 1, 1)
-        PAOS_CASE(256, 16, 8, 8, 1, 1)
-        PAOS_CASE(512, 8, 2, 8, 4, 1)
-        PAOS_CASE(1024, 16, 2, 8, 4, 1)
+        PAOS_CASE(256, 16, 4, 4, 2, 2)
+        PAOS_CASE(512, 8, 2, 2, 4, 4)
+        PAOS_CASE(1024, 16, 2, 4, 4, 2)
         PAOS_CASE(2048, 16, 1, 2, 4, 2)
         PAOS_CASE(4096, 16, 1, 2, 2, 1)
         default: return cudaErrorInvalidValue;

@@ -87,7 +87,7 @@ class Sweep:
         self.rdtype = torch.float64 if dtype == "complex128" else torch.float32
         self.streams = [torch.cuda.Stream(device=self.tdev) for _ in range(slots)]
         self.wfos = [WFO(1.0, 1.0e-6, self.n, 1.0, device=self.device, dtype=dtype, stream=s) for s in self.streams]
-        self.events = [None] * slots
+        self._pool = None
 
     def empty_stack(self, count, host=False):
         torch = self.torch
@@ -95,7 +95,7 @@ class Sweep:
             return torch.empty((count, self.n, self.n), dtype=self.rdtype, pin_memory=True)
         return torch.empty((count, self.n, self.n), dtype=self.rdtype, device=self.tdev)
 
-    def run(self, jobs, out=None, host_out=None, psd_noise=None, native=True, cache_compiled=True):
+    def run(self, jobs, out=None, host_out=None, psd_noise=None, native=True, cache_compiled=True, threads=True):
         """Propagate ``jobs``; the last saved surface of job k is read out (``what``) into ``out[k]``.
 
         ``out``: device stack (allocated when None).  ``host_out``: optional pinned host stack that also receives
@@ -110,11 +110,12 @@ class Sweep:
         if out is None:
             out = self.empty_stack(len(jobs))
         code = READS[self.what]
-        meta = []
         nslots = len(self.wfos)
         from . import chain as chain_mod
 
-        for k, job in enumerate(jobs):
+        meta = [None] * len(jobs)
+
+        def do_job(k, job):
             s = k % nslots
             wfo, stream = self.wfos[s], self.streams[s]
             dst = out[k]
@@ -128,32 +129,41 @@ class Sweep:
                 for idx in cc.saved:
                     cc.set_readout(idx, -1, None)
                 cc.set_readout(cc.saved[-1], code, dst.data_ptr())
-                snaps = chain_mod.run_compiled(wfo, job, cc)
-                last = snaps[-1]
-                last["tag"] = job.get("tag", str(k))
-                meta.append(last)
-                if host_out is not None:
-                    with torch.cuda.stream(stream):
-                        host_out[k % host_out.shape[0]].copy_(dst, non_blocking=True)
-                continue
+                last = chain_mod.run_compiled(wfo, job, cc)[-1]
+            else:
+                def snapshot(w, item):
+                    _lib.check(_lib.lib.paos_wfo_read_device(w._handle, code, C.c_void_p(dst.data_ptr())))
+                    return dict(wz=w.wz, distancetofocus=w.distancetofocus, fratio=w.fratio, dx=w.dx, dy=w.dy, wl=w.wl,
+                                extent=w.extent, propagator=w.propagator)
 
-            def snapshot(w, item, dst=dst):
-                _lib.check(_lib.lib.paos_wfo_read_device(w._handle, code, C.c_void_p(dst.data_ptr())))
-                return dict(wz=w.wz, distancetofocus=w.distancetofocus, fratio=w.fratio, dx=w.dx, dy=w.dy, wl=w.wl,
-                            extent=w.extent, propagator=w.propagator)
-
-            noise = None
-            if psd_noise is not None:
-                noise = psd_noise(job)
-            res = run(job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"],
-                      job["opt_chain"], wfo=wfo, snapshot=snapshot, psd_noise=noise)
-            last = res[max(res.keys())] if res else {}
-            last = {k2: v for k2, v in last.items() if k2 not in ("aperture", "wfe")}
+                res = run(job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"],
+                          job["opt_chain"], wfo=wfo, snapshot=snapshot, psd_noise=psd_noise(job) if psd_noise is not None else None)
+                last = res[max(res.keys())] if res else {}
+                last = {k2: v for k2, v in last.items() if k2 not in ("aperture", "wfe")}
             last["tag"] = job.get("tag", str(k))
-            meta.append(last)
+            meta[k] = last
             if host_out is not None:
                 with torch.cuda.stream(stream):
-                    host_out[k].copy_(dst, non_blocking=True)
+                    host_out[k % host_out.shape[0]].copy_(dst, non_blocking=True)
+
+        def do_slot(s):
+            # one host thread per slot: the C++ planner and the launches run without the GIL (ctypes releases it),
+            # so the slots' host work overlaps; jobs of a slot stay in order on the slot's stream
+            torch.cuda.set_device(self.device)
+            for k in range(s, len(jobs), nslots):
+                do_job(k, jobs[k])
+
+        distinct = len({id(j) for j in jobs}) == len(jobs)  # a job dict caches per-call native state
+        if threads and distinct and nslots > 1 and len(jobs) >= 2 * nslots:
+            if self._pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+
+                self._pool = ThreadPoolExecutor(max_workers=nslots)
+            for f in [self._pool.submit(do_slot, s) for s in range(nslots)]:
+                f.result()
+        else:
+            for k, job in enumerate(jobs):
+                do_job(k, job)
         for stream in self.streams:
             stream.synchronize()
         return out, meta

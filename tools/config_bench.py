@@ -27,7 +27,7 @@ def main():
 
     tmp = tempfile.mkdtemp(prefix="paos_cfg_")
     cases = {
-        "hubble": lambda: (configs.hubble(light_output=True) * 64, None),
+        "hubble": lambda: ([configs.hubble(light_output=True)[0] for _ in range(64)], None),
         "airs512": lambda: (configs.airs_ch0(grid=512, n_wl=256), None),
         "airs1024": lambda: (configs.airs_ch0(grid=1024, n_wl=128), None),
         "airs4096": lambda: (configs.airs_ch0(grid=4096, n_wl=16), None),
