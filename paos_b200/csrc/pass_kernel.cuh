@@ -252,25 +252,36 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
             }
         }
         if (pos == P.nfft) break;
-        const bool inv = P.dir[pos] < 0;
-        if (inv) {
+        // the inverse transform is the forward one on swapped (re, im); with the direction known at compile time
+        // inside each branch the swaps are register renaming, not moves
+        if (P.dir[pos] < 0) {
 #pragma unroll
             for (int j = 0; j < E; ++j) v[j] = C<R>(v[j].y, v[j].x);
-        }
-        {
-            // pull the next position's phase table into L1 while this transform runs (one 128-byte line per
-            // prefetch; the table is N complex values, shared by every line of the pass)
-            const char* nxt = reinterpret_cast<const char*>(P.tab[pos + 1]);
-            if (nxt) {
-                constexpr int LINES = N * (int)sizeof(C<R>) / 128;
+            {
+                // pull the next position's phase table into L1 while this transform runs (one 128-byte line per
+                // prefetch; the table is N complex values, shared by every line of the pass)
+                const char* nxt = reinterpret_cast<const char*>(P.tab[pos + 1]);
+                if (nxt) {
+                    constexpr int LINES = N * (int)sizeof(C<R>) / 128;
 #pragma unroll
-                for (int i = t; i < LINES; i += T) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + (size_t)i * 128));
+                    for (int i = t; i < LINES; i += T) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + (size_t)i * 128));
+                }
             }
-        }
-        line_fft_fwd<G, R>(v, t, sm, tw1, tw2, sync);
-        if (inv) {
+            line_fft_fwd<G, R>(v, t, sm, tw1, tw2, sync);
 #pragma unroll
             for (int j = 0; j < E; ++j) v[j] = C<R>(v[j].y, v[j].x);
+        } else {
+            {
+                // pull the next position's phase table into L1 while this transform runs (one 128-byte line per
+                // prefetch; the table is N complex values, shared by every line of the pass)
+                const char* nxt = reinterpret_cast<const char*>(P.tab[pos + 1]);
+                if (nxt) {
+                    constexpr int LINES = N * (int)sizeof(C<R>) / 128;
+#pragma unroll
+                    for (int i = t; i < LINES; i += T) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + (size_t)i * 128));
+                }
+            }
+            line_fft_fwd<G, R>(v, t, sm, tw1, tw2, sync);
         }
     }
     if (P.ctab_out) {

@@ -1,0 +1,109 @@
+"""Full-size (2048^2, 4096^2) checks through size-independent properties -- the numpy oracle needs ~30 s per chain at
+2048^2, so at BASELINE.json's sizes the CUDA path is checked against invariants of the operators themselves, plus
+ONE oracle comparison of the headline chain."""
+import numpy as np
+import pytest
+
+from helpers import TOL, random_field, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [2048, 4096])
+def test_ptp_there_and_back_is_identity(n):
+    import paos_b200
+
+    x = random_field(n, 3)
+    w = paos_b200.WFO(1.0, 3e-6, n, 4)
+    w.wfo = x
+    w.ptp(2500.0)
+    mid = w.wfo
+    assert relerr(mid, x) > 1e-3  # it did something
+    assert abs(np.sum(np.abs(mid) ** 2) / np.sum(np.abs(x) ** 2) - 1.0) < 1e-12  # unitary
+    w.ptp(-2500.0)
+    assert relerr(w.wfo, x) <= 1e-12
+
+
+@pytest.mark.parametrize("n", [2048, 4096])
+def test_wts_stw_round_trip_and_energy(n):
+    import paos_b200
+
+    x = random_field(n, 4)
+    w = paos_b200.WFO(1.0, 3e-6, n, 4)
+    dx0 = w.dx
+    w.wfo = x
+    w.wts(3.0e6)
+    far = w.wfo
+    assert abs(np.sum(np.abs(far) ** 2) / np.sum(np.abs(x) ** 2) - 1.0) < 1e-12
+    w.stw(-3.0e6)  # back to the waist: inverse transform, conjugate chirp
+    assert abs(w.dx / dx0 - 1.0) < 1e-14
+    assert relerr(w.wfo, x) <= 1e-11
+
+
+def test_linearity_of_a_fused_chain_2048():
+    import paos_b200
+
+    n = 2048
+
+    def chain(field):
+        w = paos_b200.WFO(1.0, 2e-6, n, 4)
+        w.wfo = field
+        w.aperture(0.0, 0.0, hx=0.9, hy=0.7, shape="elliptical")
+        w.ptp(800.0)
+        w.aperture(0.05, 0.0, hx=0.2, hy=0.1, shape="rectangular", obscuration=True)
+        w.lens(5.0)
+        w.propagate(5.0)
+        return w.wfo
+
+    f1, f2 = random_field(n, 5), random_field(n, 6)
+    a, b = 0.3 - 0.2j, -1.1 + 0.7j
+    lhs = chain(a * f1 + b * f2)
+    rhs = a * chain(f1) + b * chain(f2)
+    assert relerr(lhs, rhs) <= 1e-12
+
+
+def test_airy_pattern_known_answer_2048():
+    """Circular pupil + lens + propagation to focus: the image-plane PSF is the Airy pattern (2 J1(r)/r)^2, the overlay
+    the reference draws in paos/core/plot.py:457-462."""
+    from scipy.special import j1
+
+    import paos_b200
+
+    n, D, wl, fl, zoom = 2048, 1.0, 1.0e-6, 10.0, 8
+    w = paos_b200.WFO(D, wl, n, zoom)
+    w.aperture(0.0, 0.0, r=D / 2, shape="circular")
+    w.make_stop()
+    w.lens(fl)
+    w.propagate(fl)
+    psf = w.psf
+    assert abs(psf.sum() - 1.0) < 1e-9
+    c = n // 2
+    cut = psf[c, c:c + 200] / psf[c, c]
+    r = np.pi * D * (np.arange(200) * w.dx) / (wl * fl)
+    airy = np.ones_like(r)
+    airy[1:] = (2 * j1(r[1:]) / r[1:]) ** 2
+    # the sampled pupil is a pixelated disc (256 px across at zoom 8): agreement to a few 1e-4 of the peak
+    assert np.max(np.abs(cut - airy)) < 2e-3
+
+
+def test_headline_chain_2048_against_oracle():
+    """One wavelength of the headline workload (AIRS-CH0, 2048^2, IMAGE_PLANE only) against the numpy oracle."""
+    import paos_b200
+    from oracle import paos_np
+    from paos_b200 import configs
+    from paos_b200.sweep import Sweep
+
+    job = configs.airs_ch0(grid=2048, n_wl=256)[137]
+    args = (job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"], job["opt_chain"])
+    ref = paos_np.run(*args)
+    ref_amp = ref[max(ref)]["amplitude"]
+    got = paos_b200.run(*args, keys=("amplitude",))
+    assert relerr(got[max(got)]["amplitude"], ref_amp) <= TOL["complex128"]
+    # the same job through the batch front-end (native chain runner, |.|^2 read-out)
+    sw = Sweep(2048, slots=1, what="psf")
+    out, meta = sw.run([job])
+    assert relerr(out[0].cpu().numpy(), ref_amp**2) <= TOL["complex128"]
+    assert meta[0]["dx"] == pytest.approx(ref[max(ref)]["dx"], rel=1e-13)
+    # and in the stated single-precision mode
+    got32 = paos_b200.run(*args, keys=("amplitude",), dtype="complex64")
+    assert relerr(got32[max(got32)]["amplitude"], ref_amp) <= TOL["complex64"]
