@@ -33,6 +33,7 @@ extern "C" {
 #endif
 
 #define PAOS_ABI_VERSION 1
+#define PAOS_MAX_CHAINED_FFTS 16 /* line FFTs one pass kernel can chain */
 
 enum {
     PAOS_OK = 0,
@@ -156,7 +157,7 @@ typedef struct paos_surface {
     int read_what;         /* PAOS_READ_* to materialise at this surface when save != 0, -1 = none */
     int zernike_terms;
     int zernike_origin;    /* 0 = 'x', 1 = 'y' */
-    int pad0;
+    int screen_on_device;  /* PAOS_SURF_SCREEN: `screen` is a device pointer that stays valid until the chain has run */
     double ap_xrad, ap_yrad, ap_xc, ap_yc;      /* as in opt_chain[..]["aperture"]; NaN centre = follow the chief ray */
     double abcd_t[4], abcd_s[4];                /* row-major A, B, C, D of item["ABCDt"], item["ABCDs"]   */
     double cout_t;                              /* item["ABCDt"].cout (+1 / -1)                         */
@@ -166,7 +167,7 @@ typedef struct paos_surface {
     uint64_t psd_seed;
     const int *zernike_m, *zernike_n;           /* host arrays [zernike_terms]                           */
     const double *zernike_coef;                 /* Z[k] * norm[k]                                        */
-    const double *screen;                       /* PAOS_SURF_SCREEN: n*n host doubles                    */
+    const double *screen;                       /* PAOS_SURF_SCREEN: n*n doubles (host, or device if flagged) */
     const double *psd_noise1, *psd_noise2;      /* host arrays or NULL (device RNG from psd_seed)        */
     void *read_dst;                             /* device destination of the read-out                    */
 } paos_surface;
@@ -198,7 +199,7 @@ int paos_wfo_enable_timing(paos_wfo *w, int enable);
 /* sum of pass-kernel device times (ms) and number of timed launches since the last call */
 int paos_wfo_timing(paos_wfo *w, double *pass_ms, uint64_t *pass_launches);
 /* the same split by pass kind: col = 0 row pass / 1 column pass, nfft = line FFTs chained in the pass
- * (0..8); reset != 0 clears the bucket after reading it */
+ * (0..PAOS_MAX_CHAINED_FFTS); reset != 0 clears the bucket after reading it */
 int paos_wfo_timing_detail(paos_wfo *w, int col, int nfft, double *ms, uint64_t *launches, int reset);
 
 #ifdef __cplusplus

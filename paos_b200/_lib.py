@@ -16,6 +16,7 @@ PAOS_C128, PAOS_C64 = 0, 1
 READ_WFO, READ_AMPLITUDE, READ_PHASE, READ_PSF = 0, 1, 2, 3
 SHAPE_ELLIPSE, SHAPE_RECT = 0, 1
 ABI_VERSION = 1
+MAX_CHAINED_FFTS = 16
 
 
 class PaosError(RuntimeError):

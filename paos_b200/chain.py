@@ -20,7 +20,7 @@ class Surface(C.Structure):
     _fields_ = [
         ("type", C.c_int), ("is_stop", C.c_int), ("save", C.c_int), ("has_aperture", C.c_int), ("ap_shape", C.c_int),
         ("ap_obscuration", C.c_int), ("read_what", C.c_int), ("zernike_terms", C.c_int), ("zernike_origin", C.c_int),
-        ("pad0", C.c_int),
+        ("screen_on_device", C.c_int),
         ("ap_xrad", C.c_double), ("ap_yrad", C.c_double), ("ap_xc", C.c_double), ("ap_yc", C.c_double),
         ("abcd_t", C.c_double * 4), ("abcd_s", C.c_double * 4), ("cout_t", C.c_double),
         ("xdec", C.c_double), ("ydec", C.c_double), ("xrot", C.c_double), ("yrot", C.c_double),
@@ -48,7 +48,7 @@ class Snapshot(C.Structure):
 class CompiledChain:
     """``paos_surface`` array of one job plus the host arrays it points to (kept alive here)."""
 
-    def __init__(self, opt_chain, gridsize, pupil_diameter, zoom, psd_seed=0, psd_noise=None):
+    def __init__(self, opt_chain, gridsize, pupil_diameter, zoom, psd_seed=0, psd_noise=None, device=None, screen_cache=None):
         items = list(opt_chain.values())
         self.n = int(gridsize)
         self.count = len(items)
@@ -103,8 +103,23 @@ class CompiledChain:
                 s.zernike_radius = float(item["Zradius"])
             elif s.type == SURF_SCREEN:
                 screen = _on_grid_sag(item, self.n, pupil_diameter, zoom)
-                self.keep.append(screen)
-                s.screen = screen.ctypes.data_as(C.POINTER(C.c_double))
+                if device is None:
+                    self.keep.append(screen)
+                    s.screen = screen.ctypes.data_as(C.POINTER(C.c_double))
+                else:
+                    # upload once and share between jobs that carry the same map (one per wavelength in a sweep)
+                    import torch
+
+                    key = (screen.shape, hash(screen[::61, ::53].tobytes()), float(screen.sum()))
+                    cache = screen_cache if screen_cache is not None else {}
+                    dev = cache.get(key)
+                    if dev is None:
+                        dev = torch.from_numpy(screen).to(torch.device("cuda", int(device)))
+                        torch.cuda.synchronize(int(device))
+                        cache[key] = dev
+                    self.keep.append(dev)
+                    s.screen = C.cast(C.c_void_p(dev.data_ptr()), C.POINTER(C.c_double))
+                    s.screen_on_device = 1
             elif s.type == SURF_PSD:
                 from .wfo import _unit_to_m
 
@@ -140,12 +155,13 @@ def _on_grid_sag(item, n, pupil_diameter, zoom):
     return np.ascontiguousarray(sag.filled(0.0), dtype=np.float64)
 
 
-def compile_job(job, psd_noise=None):
-    """Compile (and cache on the job dict) the native surface records of a job."""
+def compile_job(job, psd_noise=None, device=None, screen_cache=None):
+    """Compile (and cache on the job dict) the native surface records of a job.  With ``device`` the grid-sag maps are
+    uploaded once (shared through ``screen_cache``) instead of travelling from host memory on every run."""
     cc = job.get("_compiled")
     if cc is None or psd_noise is not None:
         cc = CompiledChain(job["opt_chain"], job["gridsize"], job["pupil_diameter"], job["zoom"],
-                           psd_seed=job.get("psd_seed", 0), psd_noise=psd_noise)
+                           psd_seed=job.get("psd_seed", 0), psd_noise=psd_noise, device=device, screen_cache=screen_cache)
         if psd_noise is None:
             job["_compiled"] = cc
     return cc

@@ -5,7 +5,7 @@
 
 namespace paosb {
 
-constexpr int KMAX = 8;   // line FFTs chained in one pass kernel
+constexpr int KMAX = 16;  // line FFTs chained in one pass kernel (= PAOS_MAX_CHAINED_FFTS of the public header)
 constexpr int GMAX = 12;  // general (non-separable) factors applied by one pass kernel
 constexpr int TERM_MAX = 8;
 constexpr int TB_MAX = 64;  // tables built by one launch of the table builder (kernel parameters may be 32 KB on sm_70+)

@@ -168,12 +168,15 @@ template <int N_, int E_> struct LineGeom {
     static_assert(R2 <= E, "middle radix must divide E");
     static constexpr int TW1 = (E - 1) * T;                 // stage-1 twiddles  [k1-1][t] = W_N^(k1*t)
     static constexpr int TW2 = (R2 > 1) ? (R2 - 1) * E : 0; // stage-2 twiddles  [k2-1][n3] = W_T^(k2*n3)
-    // line stride in the exchange buffer (complex elements) so that W interleaved lines are
-    // bank-conflict free for 16-byte accesses ("shared-memory exchange")
-    __host__ __device__ static constexpr int line_stride(int W) {
+    // Line stride in the exchange buffer (complex elements) so that W interleaved lines are bank-conflict free:
+    // a shared-memory wavefront covers 128 bytes = SLOTS complex elements (8 for complex128, 16 for complex64);
+    // with the column-minor mapping a wavefront holds SLOTS/W consecutive elements of each of the W lines, so the
+    // lines must sit SLOTS/W slots apart modulo SLOTS.
+    __host__ __device__ static constexpr int line_stride(int W, int elem_bytes) {
+        int slots = 128 / elem_bytes;
         int base = E * TP;
-        int want = (W >= 8) ? 1 : (W == 4 ? 2 : (W == 2 ? 4 : 0));
-        int pad = ((want - (base % 8)) % 8 + 8) % 8;
+        int want = (W >= slots) ? 1 : (W <= 1 ? 0 : slots / W);
+        int pad = ((want - (base % slots)) % slots + slots) % slots;
         return base + pad;
     }
 };

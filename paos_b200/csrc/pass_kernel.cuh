@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
     const int w = COL ? (tid % W) : (tid / T);
     const int t = COL ? (tid / W) : (tid % T);
     const int line = blockIdx.x * W + w;
-    C<R>* sm = smem + w * G::line_stride(COL ? W : 1);
+    C<R>* sm = smem + w * G::line_stride(COL ? W : 1, (int)sizeof(C<R>));
     auto sync = [] { __syncthreads(); };
 
     const C<R>* src = reinterpret_cast<const C<R>*>(P.src);
@@ -313,7 +313,7 @@ template <typename R, int N, int E, int W, bool COL, int MINB>
 cudaError_t launch_pass_t(const PassParams& P, const void* tw1, const void* tw2, cudaStream_t st, int device) {
     using G = LineGeom<N, E>;
     constexpr int threads = W * G::T;
-    const size_t smem = (size_t)W * G::line_stride(COL ? W : 1) * sizeof(C<R>);
+    const size_t smem = (size_t)W * G::line_stride(COL ? W : 1, (int)sizeof(C<R>)) * sizeof(C<R>);
     auto kern = pass_kernel<R, N, E, W, COL, MINB>;
     static bool configured[64] = {};  // per instantiation and device
     if (!configured[device & 63]) {

@@ -1265,7 +1265,8 @@ extern "C" int paos_chain_run(paos_wfo* w, double pupil_diameter, double wavelen
                                   s.zernike_origin, b.wl, nullptr);
             if (rc) return rc;
         } else if (s.type == PAOS_SURF_SCREEN) {
-            if ((rc = paos_wfo_phase_screen(w, s.screen, b.wl))) return rc;
+            rc = s.screen_on_device ? paos_wfo_phase_screen_device(w, s.screen, b.wl) : paos_wfo_phase_screen(w, s.screen, b.wl);
+            if (rc) return rc;
         } else if (s.type == PAOS_SURF_PSD) {
             const double f_nyq = 0.5 * std::sqrt(1.0 / sq(b.dx) + 1.0 / sq(b.dy));
             if (!(s.psd[5] <= f_nyq)) return fail(PAOS_ERR_ARG, "fmax must be less than or equal to f_Nyq (%g)", f_nyq);

@@ -88,6 +88,7 @@ class Sweep:
         self.streams = [torch.cuda.Stream(device=self.tdev) for _ in range(slots)]
         self.wfos = [WFO(1.0, 1.0e-6, self.n, 1.0, device=self.device, dtype=dtype, stream=s) for s in self.streams]
         self._pool = None
+        self._screens = {}  # device copies of grid-sag maps shared between jobs
 
     def empty_stack(self, count, host=False):
         torch = self.torch
@@ -123,7 +124,8 @@ class Sweep:
                 # whole chain planned and enqueued inside the library (paos_chain_run)
                 if not cache_compiled:
                     job.pop("_compiled", None)
-                cc = chain_mod.compile_job(job, psd_noise(job) if psd_noise is not None else None)
+                cc = chain_mod.compile_job(job, psd_noise(job) if psd_noise is not None else None, device=self.device,
+                                           screen_cache=self._screens)
                 if not cc.saved:
                     raise ValueError(f"job {job.get('tag', k)} saves no surface")
                 for idx in cc.saved:
@@ -187,7 +189,7 @@ class Sweep:
         for w in self.wfos:
             _lib.check(_lib.lib.paos_wfo_sync(w._handle))
             for col in (0, 1):
-                for nfft in range(0, 9):
+                for nfft in range(0, _lib.MAX_CHAINED_FFTS + 1):
                     ms, cnt = C.c_double(), C.c_uint64()
                     _lib.check(_lib.lib.paos_wfo_timing_detail(w._handle, col, nfft, C.byref(ms), C.byref(cnt), 1 if reset else 0))
                     if cnt.value:

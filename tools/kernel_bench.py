@@ -53,13 +53,13 @@ def main():
                 for ww in ws:
                     ww.sync()
                     for col in (0, 1):
-                        for nf in range(9):
+                        for nf in range(_lib.MAX_CHAINED_FFTS + 1):
                             _lib.lib.paos_wfo_timing_detail(ww._handle, col, nf, None, None, 1)
         out = {}
         for ww in ws:
             ww.sync()
             for col in (0, 1):
-                for nf in range(9):
+                for nf in range(_lib.MAX_CHAINED_FFTS + 1):
                     ms, cnt = C.c_double(), C.c_uint64()
                     _lib.lib.paos_wfo_timing_detail(ww._handle, col, nf, C.byref(ms), C.byref(cnt), 1)
                     if cnt.value:
