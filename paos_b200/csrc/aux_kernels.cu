@@ -41,6 +41,22 @@ __device__ __forceinline__ void phase_term(const TableTerm& tm, int k, int n, do
     sn = fma(c, re, s);
 }
 
+// number of the 32 sub-pixel centres of pixel k strictly inside (-full/2, full/2) around the centre;
+// accumulation order of the published photutils routine (x = x0 - d/2; x += d)
+__device__ __forceinline__ int subpixel_count(int k, double centre, double full) {
+    const double half = full / 2.0;
+    const double x0 = ((double)k - 0.5) - centre;
+    const double x1 = x0 + 1.0;
+    const double d = (x1 - x0) / 32.0;
+    double x = x0 - 0.5 * d;
+    int cnt = 0;
+    for (int s = 0; s < 32; ++s) {
+        x += d;
+        if (fabs(x) < half) ++cnt;
+    }
+    return cnt;
+}
+
 template <typename R>
 __global__ void build_tables_kernel(const __grid_constant__ TableBlock B) {
     const TableSpec& sp = B.spec[blockIdx.y];
@@ -48,25 +64,20 @@ __global__ void build_tables_kernel(const __grid_constant__ TableBlock B) {
     const int n = B.n;
     if (k >= n) return;
     if (sp.kind == TABLE_COUNT) {
-        // number of the 32 sub-pixel centres of pixel k strictly inside (-full/2, full/2) around the centre;
-        // accumulation order of the published photutils routine (x = x0 - d/2; x += d)
-        const double half = sp.cnt_full / 2.0;
-        const double x0 = ((double)k - 0.5) - sp.cnt_c;
-        const double x1 = x0 + 1.0;
-        const double d = (x1 - x0) / 32.0;
-        double x = x0 - 0.5 * d;
-        int cnt = 0;
-        for (int s = 0; s < 32; ++s) {
-            x += d;
-            if (fabs(x) < half) ++cnt;
-        }
+        const int cnt = subpixel_count(k, sp.cnt_c, sp.cnt_full);
         reinterpret_cast<double*>(sp.out)[k] = (double)cnt;
         return;
     }
     double re = 1.0, im = 0.0;
     for (int i = 0; i < sp.nterms; ++i) {
         double c, s;
-        phase_term(sp.terms[i], k, n, c, s);
+        if (sp.terms[i].kind == TERM_COUNT) {
+            // separable rectangular aperture: (cx/32)*(cy/32) == (cy*cx)/1024 exactly (dyadic rationals)
+            c = (double)subpixel_count(k, sp.terms[i].c1, sp.terms[i].c2) / 32.0;
+            s = 0.0;
+        } else {
+            phase_term(sp.terms[i], k, n, c, s);
+        }
         const double nr = re * c - im * s, ni = re * s + im * c;
         re = nr;
         im = ni;

@@ -49,7 +49,8 @@ struct PassParams {
 };
 
 // one separable phase term: exp(i * c1*c2 * u^2), u = (k - n/2) * d  (QSPACE)  or  (k - n/2) * (1/(n*d))  (QFREQ)
-enum TermKind : int { TERM_QSPACE = 1, TERM_QFREQ = 2 };
+// TERM_COUNT: real factor count(k)/32, count = sub-pixel centres of pixel k inside a rectangle side (c1 = centre, c2 = full side)
+enum TermKind : int { TERM_QSPACE = 1, TERM_QFREQ = 2, TERM_COUNT = 3 };
 struct TableTerm {
     int kind;
     int pad;

@@ -127,7 +127,13 @@ __device__ __forceinline__ void apply_gen(C<R>& v, const GenOp& g, int ix, int i
     double re = 1.0, im = 0.0;
     switch (g.kind) {
         case GEN_ELLIPSE: {
-            double m = ellipse_fraction(g, (double)ix, (double)iy);
+            // same FP32 interior / exterior classification as the pass kernel; exact routine only in the edge band
+            const float uq = ((float)ix - (float)g.p0) * (float)g.p2, wq = ((float)iy - (float)g.p1) * (float)g.p3;
+            const float r2 = uq * uq + wq * wq;
+            double m;
+            if (r2 <= (float)g.p5 - 1e-5f) m = 1.0;
+            else if (r2 >= (float)g.p6 + 1e-5f) m = 0.0;
+            else m = ellipse_fraction(g, (double)ix, (double)iy);
             re = g.flag ? 1.0 - m : m;
         } break;
         case GEN_RECT: {

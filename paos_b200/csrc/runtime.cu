@@ -739,6 +739,18 @@ int paos_wfo_aperture(paos_wfo* w, int shape, double ixc, double iyc, double ihx
         const double d = 0.5 * std::sqrt(g.p2 * g.p2 + g.p3 * g.p3) * (1.0 + 1e-9) + 1e-12;
         g.p5 = d < 1.0 ? (1.0 - d) * (1.0 - d) : -1.0;
         g.p6 = (1.0 + d) * (1.0 + d);
+    } else if (shape == PAOS_SHAPE_RECT && !obscuration) {
+        // a rectangular *aperture* is separable, mask = (cx[ix]/32) * (cy[iy]/32): it rides in the phase tables like a
+        // chirp and costs no pass boundary (an obscuration, 1 - mask, is not separable: general factor below)
+        Op op{};
+        op.kind = OP_PHASE;
+        op.tx.kind = op.ty.kind = TERM_COUNT;
+        op.tx.c1 = ixc;
+        op.tx.c2 = ihx;
+        op.ty.c1 = iyc;
+        op.ty.c2 = ihy;
+        w->ops.push_back(op);
+        return PAOS_OK;
     } else if (shape == PAOS_SHAPE_RECT) {
         // separable 32-sub-pixel counts, built right away into a screen buffer (2*n doubles)
         int rc = set_device(w);
@@ -781,7 +793,7 @@ int paos_wfo_make_stop(paos_wfo* w) {
     std::vector<GenOp> gens;
     while (k > 0) {
         const Op& op = w->ops[k - 1];
-        if (op.kind == OP_SIGN || op.kind == OP_PHASE) {
+        if (op.kind == OP_SIGN || (op.kind == OP_PHASE && op.tx.kind != TERM_COUNT)) {
             --k;
         } else if (op.kind == OP_GEN && op.gen.kind == GEN_SCREEN) {
             --k;
