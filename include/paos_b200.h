@@ -115,6 +115,17 @@ int paos_wfo_phase_screen_device(paos_wfo *w, const double *dev_screen, double w
 int paos_wfo_zernike(paos_wfo *w, int nterms, const int *m, const int *n, const double *coef,
                      double radius, double dx, double dy, double offset, int origin, double wl,
                      double *wfe_host_out);
+/* the same with a pupil mask (wfo.py:624-628: numpy masked-array convention, n*n host bytes, non-zero = masked
+ * pixel -> wfe 0 there); host_mask may be NULL */
+int paos_wfo_zernike_masked(paos_wfo *w, int nterms, const int *m, const int *n, const double *coef,
+                            double radius, double dx, double dy, double offset, int origin, double wl,
+                            const unsigned char *host_mask, double *wfe_host_out);
+/* zernike.py:293-317 (Zernike.cov), the reduction behind PolyOrthoNorm (zernike.py:388-402):
+ * cov[i*K+j] = mean over the unmasked pixels (rho <= 1 and mask == 0) of norm[i]*Z_i * norm[j]*Z_j, K = nterms <= 64.
+ * Blocking (returns the K x K matrix in host memory); does not touch the wavefront.  norm may be NULL (ones). */
+int paos_zernike_cov(paos_wfo *w, int nterms, const int *m, const int *n, const double *norm, double radius,
+                     double dx, double dy, double offset, int origin, const unsigned char *host_mask,
+                     double *cov_host_out);
 /* wfo.py:873-949 + psd.py:113-148: surface-error screen with power spectrum A/(B+(f/fknee)^C) between
  * fmin and fmax plus white roughness SR, times 2*unit_scale, applied as a phase screen.
  * noise1/noise2: n*n host doubles replacing the reference's two np.random.randn draws (bit-parity

@@ -101,7 +101,22 @@ def elliptical_mask(shape, xc, yc, a, b, theta=0.0):
     band = (~inside) & (np.sqrt(u0 * u0 + v0 * v0) < 1.0 + np.hypot(reach, reach) * 1.5 + 1e-9)
     yy, xx = np.nonzero(band)
     if yy.size:
-        img[yy, xx] = ellipse_pixel_fraction(xx, yy, xc, yc, a, b, theta)
+        frac = ellipse_pixel_fraction(xx, yy, xc, yc, a, b, theta)
+        # The published routine returns EXACTLY 0 for a pixel that does not reach the ellipse and exactly 1 for a pixel
+        # inside it (explicit geometric branches), which matters wherever the mask is used as a boolean
+        # (run.py:137-141).  The signed-sum formula above leaves ~1e-19 residues there, so decide those two cases
+        # geometrically: nearest / farthest point of the pixel from the centre in the unit-circle frame.
+        if theta == 0.0:
+            u0, u1 = (xx - 0.5 - xc) / a, (xx + 0.5 - xc) / a
+            v0, v1 = (yy - 0.5 - yc) / b, (yy + 0.5 - yc) / b
+            un = np.where((u0 <= 0) & (u1 >= 0), 0.0, np.minimum(np.abs(u0), np.abs(u1)))
+            vn = np.where((v0 <= 0) & (v1 >= 0), 0.0, np.minimum(np.abs(v0), np.abs(v1)))
+            uf, vf = np.maximum(np.abs(u0), np.abs(u1)), np.maximum(np.abs(v0), np.abs(v1))
+            frac = np.where(un * un + vn * vn >= 1.0, 0.0, frac)
+            frac = np.where(uf * uf + vf * vf <= 1.0, 1.0, frac)
+        else:
+            frac = np.where(frac < 1e-14, 0.0, np.where(frac > 1.0 - 1e-14, 1.0, frac))
+        img[yy, xx] = frac
     return img
 
 

@@ -1,6 +1,6 @@
 """ctypes binding of ``libpaos_b200.so`` (the C ABI declared in ``include/paos_b200.h``).
 
-There is deliberately no fallback: if the shared library has not been built (``python -m paos_b200.build``)
+There is deliberately no fallback: if the shared library has not been built (``python paos_b200/build.py``)
 importing this module raises, and every entry point fails with ``PaosCudaError`` when no sm_100 device is
 usable.  Nothing in this package computes a wavefront on the CPU.
 """
@@ -60,6 +60,8 @@ SIGNATURES = {
     "paos_wfo_phase_screen": (_i, [_vp, _vp, _d]),
     "paos_wfo_phase_screen_device": (_i, [_vp, _vp, _d]),
     "paos_wfo_zernike": (_i, [_vp, _i, _ip, _ip, _dp, _d, _d, _d, _d, _i, _d, _vp]),
+    "paos_wfo_zernike_masked": (_i, [_vp, _i, _ip, _ip, _dp, _d, _d, _d, _d, _i, _d, _vp, _vp]),
+    "paos_zernike_cov": (_i, [_vp, _i, _ip, _ip, _vp, _d, _d, _d, _d, _i, _vp, _vp]),
     "paos_wfo_psd": (_i, [_vp, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _vp, _vp, C.c_uint64, _vp]),
     "paos_wfo_ptp": (_i, [_vp, _d, _d, _d, _d]),
     "paos_wfo_stw": (_i, [_vp, _d, _d, _d, _d]),
@@ -74,7 +76,7 @@ SIGNATURES = {
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
-        f"{LIB_PATH} is missing: build it with `python -m paos_b200.build` (nvcc, sm_100a). "
+        f"{LIB_PATH} is missing: build it with `python paos_b200/build.py` (nvcc, sm_100a). "
         "paos_b200 has no CPU fallback."
     )
 

@@ -1,6 +1,7 @@
 """Build libpaos_b200.so in-tree with nvcc for sm_100a (no torch, no JIT cache: the .so travels with the repo).
 
-Usage: ``python -m paos_b200.build [--force]``.  ``__graft_entry__.build()`` calls :func:`build`.
+Usage: ``python paos_b200/build.py [--force]`` (run it by path: ``python -m paos_b200.build`` imports the package first,
+which needs an up-to-date library).  ``__graft_entry__.build()`` calls :func:`build`.
 """
 import os
 import subprocess

@@ -193,50 +193,139 @@ __device__ __forceinline__ double jacobi_m0(int k, int m, double x) {
     return p;
 }
 
-__global__ void __launch_bounds__(256) zernike_kernel(const __grid_constant__ ZernParams Z, double* __restrict__ out) {
+// polar unit vector and rho of one pixel; returns false outside the unit disc (rho > 1 is masked: zernike.py:85)
+__device__ __forceinline__ bool zern_polar(const ZernParams& Z, int ix, int iy, double& rho, double& c1, double& s1) {
+    const int n = Z.n;
+    const double x = (double)(ix - n / 2) * Z.dx, y = (double)(iy - n / 2) * Z.dy;
+    const double r = sqrt(x * x + y * y);
+    rho = r / Z.radius;
+    if (!(rho <= 1.0)) return false;
+    // unit vector of the polar angle (origin x: atan2(y, x); origin y: atan2(x, y)), rotated by the offset
+    double c0, s0;
+    if (r > 0.0) {
+        c0 = (Z.origin == 0 ? x : y) / r;
+        s0 = (Z.origin == 0 ? y : x) / r;
+    } else {
+        c0 = 1.0;
+        s0 = 0.0;
+    }
+    c1 = c0 * Z.cos_off - s0 * Z.sin_off;
+    s1 = s0 * Z.cos_off + c0 * Z.sin_off;
+    return true;
+}
+
+// k-th polynomial times coef[k] (coef carries Z[k]*norm[k]*binom*(-1)^k, or norm*binom*(-1)^k for the covariance)
+__device__ __forceinline__ double zern_term(const ZernParams& Z, int k, double rho, double c1, double s1, double xj) {
+    const int m = Z.m[k], am = m < 0 ? -m : m, kr = (Z.nn[k] - am) / 2;
+    double rp = 1.0, cm = 1.0, sm = 0.0;  // rho^|m| and cos/sin(|m| phi) by repeated multiplication
+    for (int q = 0; q < am; ++q) {
+        rp *= rho;
+        const double nc = cm * c1 - sm * s1;
+        sm = sm * c1 + cm * s1;
+        cm = nc;
+    }
+    const double ang = (m > 0) ? cm : ((m < 0) ? sm : 1.0);
+    return Z.coef[k] * (rp * jacobi_m0(kr, am, xj)) * ang;
+}
+
+__global__ void __launch_bounds__(256) zernike_kernel(const __grid_constant__ ZernParams Z, const unsigned char* __restrict__ mask,
+                                                      double* __restrict__ out) {
     const int n = Z.n;
     const size_t total = (size_t)n * n;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int iy = (int)(i / n), ix = (int)(i % n);
-        const double x = (double)(ix - n / 2) * Z.dx, y = (double)(iy - n / 2) * Z.dy;
-        const double r = sqrt(x * x + y * y);
-        const double rho = r / Z.radius;
-        double wfe = 0.0;
-        if (rho <= 1.0) {
-            // unit vector of the polar angle (origin x: atan2(y, x); origin y: atan2(x, y)), rotated by the offset
-            double c0, s0;
-            if (r > 0.0) {
-                c0 = (Z.origin == 0 ? x : y) / r;
-                s0 = (Z.origin == 0 ? y : x) / r;
-            } else {
-                c0 = 1.0;
-                s0 = 0.0;
-            }
-            const double c1 = c0 * Z.cos_off - s0 * Z.sin_off, s1 = s0 * Z.cos_off + c0 * Z.sin_off;
+        double rho, c1, s1, wfe = 0.0;
+        if (zern_polar(Z, ix, iy, rho, c1, s1) && !(mask && mask[i])) {
             const double xj = 1.0 - 2.0 * (rho * rho);
-            for (int k = 0; k < Z.K; ++k) {
-                const int m = Z.m[k], am = m < 0 ? -m : m, kr = (Z.nn[k] - am) / 2;
-                // rho^|m| and cos/sin(|m| phi) by repeated multiplication
-                double rp = 1.0, cm = 1.0, sm = 0.0;
-                for (int q = 0; q < am; ++q) {
-                    rp *= rho;
-                    const double nc = cm * c1 - sm * s1;
-                    sm = sm * c1 + cm * s1;
-                    cm = nc;
-                }
-                const double ang = (m > 0) ? cm : ((m < 0) ? sm : 1.0);
-                wfe += Z.coef[k] * (rp * jacobi_m0(kr, am, xj)) * ang;
-            }
+            for (int k = 0; k < Z.K; ++k) wfe += zern_term(Z, k, rho, c1, s1, xj);
         }
         if (Z.accumulate) out[i] += wfe;
         else out[i] = wfe;
     }
 }
 
-cudaError_t launch_zernike(const ZernParams& Z, double* out, cudaStream_t st) {
+cudaError_t launch_zernike(const ZernParams& Z, const unsigned char* mask, double* out, cudaStream_t st) {
     const size_t total = (size_t)Z.n * Z.n;
     const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-    zernike_kernel<<<blocks, 256, 0, st>>>(Z, out);
+    zernike_kernel<<<blocks, 256, 0, st>>>(Z, mask, out);
+    return cudaGetLastError();
+}
+
+// ---- Zernike covariance (zernike.py:293-317): sums of Z_i*Z_j over the unmasked pixels ---------------------
+// One CTA walks over tiles of COV_TILE pixels: every polynomial of every pixel of the tile goes to shared memory,
+// then each thread accumulates the dot products of the (i <= j) pairs it owns.  Per-CTA partial sums (and the
+// unmasked pixel count in slot K*K) go to `partial[block][K*K+1]`; the host adds the blocks up.
+constexpr int COV_TILE = 128;
+__global__ void __launch_bounds__(256) zernike_cov_kernel(const __grid_constant__ ZernParams Z, const unsigned char* __restrict__ mask,
+                                                          double* __restrict__ partial) {
+    extern __shared__ double zs[];  // [K][COV_TILE + 1]
+    constexpr int LD = COV_TILE + 1;
+    const int K = Z.K, n = Z.n, npairs = K * (K + 1) / 2;
+    const size_t total = (size_t)n * n;
+    constexpr int PMAX = 9;  // pairs per thread: K <= 64 -> 2080 pairs / 256 threads
+    double acc[PMAX];
+    int pi_[PMAX], pj_[PMAX];
+#pragma unroll
+    for (int q = 0; q < PMAX; ++q) {
+        acc[q] = 0.0;
+        const int pidx = threadIdx.x + q * 256;
+        int i = 0, rem = pidx;  // unrank (i <= j) from the pair index
+        if (pidx < npairs) {
+            while (rem >= K - i) {
+                rem -= K - i;
+                ++i;
+            }
+        }
+        pi_[q] = i;
+        pj_[q] = i + rem;
+    }
+    double count = 0.0;
+    for (size_t base = (size_t)blockIdx.x * COV_TILE; base < total; base += (size_t)gridDim.x * COV_TILE) {
+        __syncthreads();
+        if (threadIdx.x < COV_TILE) {
+            const size_t i = base + threadIdx.x;
+            double rho = 2.0, c1 = 1.0, s1 = 0.0;
+            bool ok = i < total;
+            if (ok) ok = zern_polar(Z, (int)(i % n), (int)(i / n), rho, c1, s1) && !(mask && mask[i]);
+            const double xj = 1.0 - 2.0 * (rho * rho);
+            for (int k = 0; k < K; ++k) zs[k * LD + threadIdx.x] = ok ? zern_term(Z, k, rho, c1, s1, xj) : 0.0;
+            if (ok) count += 1.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PMAX; ++q) {
+            if (threadIdx.x + q * 256 < npairs) {
+                const double* a = zs + pi_[q] * LD;
+                const double* b = zs + pj_[q] * LD;
+                double s = 0.0;
+                for (int p2 = 0; p2 < COV_TILE; ++p2) s += a[p2] * b[p2];
+                acc[q] += s;
+            }
+        }
+    }
+    double* mine = partial + (size_t)blockIdx.x * (K * K + 1);
+#pragma unroll
+    for (int q = 0; q < PMAX; ++q)
+        if (threadIdx.x + q * 256 < npairs) {
+            mine[pi_[q] * K + pj_[q]] = acc[q];
+            mine[pj_[q] * K + pi_[q]] = acc[q];
+        }
+    // unmasked pixel count of this CTA
+    __shared__ double red[256];
+    red[threadIdx.x] = count;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) mine[K * K] = red[0];
+}
+
+cudaError_t launch_zernike_cov(const ZernParams& Z, const unsigned char* mask, double* partial, int blocks, cudaStream_t st) {
+    const size_t smem = (size_t)Z.K * (COV_TILE + 1) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(zernike_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    zernike_cov_kernel<<<blocks, 256, smem, st>>>(Z, mask, partial);
     return cudaGetLastError();
 }
 

@@ -7,7 +7,8 @@ cudaError_t launch_build_tables(const TableBlock& B, cudaStream_t st);
 cudaError_t launch_norm2(const void* src, int n, int dtype, const GenOp* gen, int ngen, double* partials,
                          int npartials, double* out_slot, cudaStream_t st);
 cudaError_t launch_readout(const void* src, int n, int dtype, int what, void* out, cudaStream_t st);
-cudaError_t launch_zernike(const ZernParams& Z, double* out, cudaStream_t st);
+cudaError_t launch_zernike(const ZernParams& Z, const unsigned char* mask, double* out, cudaStream_t st);
+cudaError_t launch_zernike_cov(const ZernParams& Z, const unsigned char* mask, double* partial, int blocks, cudaStream_t st);
 cudaError_t launch_real_to_complex(const double* src, int n, int dtype, void* dst, cudaStream_t st);
 cudaError_t launch_psd_finalize(const void* f, int n, int dtype, const double* noise2, double SR, double unit,
                                 double* out, cudaStream_t st);

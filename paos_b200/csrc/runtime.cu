@@ -863,8 +863,45 @@ static double binom(int n, int k) {
     return b;
 }
 
-int paos_wfo_zernike(paos_wfo* w, int nterms, const int* m, const int* n, const double* coef, double radius, double dx,
-                     double dy, double offset, int origin, double wl, double* wfe_host_out) {
+// fill the kernel parameters of one chunk of <= ZERN_MAX terms; coef_in may be NULL (coefficient 1)
+static int fill_zern(paos_wfo* w, ZernParams& Z, int s, int nterms, const int* m, const int* n, const double* coef_in,
+                     const double* norm_in, double radius, double dx, double dy, double offset, int origin) {
+    Z = ZernParams{};
+    Z.K = std::min(ZERN_MAX, nterms - s);
+    Z.origin = origin;
+    Z.n = w->n;
+    Z.accumulate = s > 0;
+    Z.radius = radius;
+    Z.dx = dx;
+    Z.dy = dy;
+    Z.cos_off = std::cos(offset);
+    Z.sin_off = std::sin(offset);
+    for (int k = 0; k < Z.K; ++k) {
+        const int mm = m[s + k], nn = n[s + k], am = mm < 0 ? -mm : mm;
+        if (nn < am || ((nn - am) & 1)) return fail(PAOS_ERR_ARG, "invalid Zernike (m, n) = (%d, %d)", mm, nn);
+        const int kr = (nn - am) / 2;
+        Z.m[k] = mm;
+        Z.nn[k] = nn;
+        // scipy's eval_jacobi returns binom(k+alpha, k) * recurrence; (-1)^k from zernike.py:245-247
+        Z.coef[k] = (coef_in ? coef_in[s + k] : 1.0) * (norm_in ? norm_in[s + k] : 1.0) * binom(kr + am, kr) * ((kr & 1) ? -1.0 : 1.0);
+    }
+    return PAOS_OK;
+}
+
+// pixel mask (numpy masked-array convention: non-zero = masked) to the device; NULL stays NULL
+static int upload_mask(paos_wfo* w, const unsigned char* host_mask, unsigned char** dev) {
+    *dev = nullptr;
+    if (!host_mask) return PAOS_OK;
+    double* buf;
+    int rc = get_screen(w, &buf);  // n*n doubles are more than enough for n*n bytes
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(buf, host_mask, (size_t)w->n * w->n, cudaMemcpyHostToDevice, w->stream));
+    *dev = reinterpret_cast<unsigned char*>(buf);
+    return PAOS_OK;
+}
+
+int paos_wfo_zernike_masked(paos_wfo* w, int nterms, const int* m, const int* n, const double* coef, double radius, double dx,
+                            double dy, double offset, int origin, double wl, const unsigned char* host_mask, double* wfe_host_out) {
     if (!w || !m || !n || !coef) return fail(PAOS_ERR_ARG, "null argument");
     if (nterms < 1) return fail(PAOS_ERR_ARG, "need at least one Zernike term");
     if (origin != 0 && origin != 1) return fail(PAOS_ERR_ARG, "origin must be 0 ('x') or 1 ('y')");
@@ -874,27 +911,12 @@ int paos_wfo_zernike(paos_wfo* w, int nterms, const int* m, const int* n, const 
     double* screen;
     rc = get_screen(w, &screen);
     if (rc) return rc;
+    unsigned char* dmask;
+    if ((rc = upload_mask(w, host_mask, &dmask))) return rc;
     for (int s = 0; s < nterms; s += ZERN_MAX) {
-        ZernParams Z{};
-        Z.K = std::min(ZERN_MAX, nterms - s);
-        Z.origin = origin;
-        Z.n = w->n;
-        Z.accumulate = s > 0;
-        Z.radius = radius;
-        Z.dx = dx;
-        Z.dy = dy;
-        Z.cos_off = std::cos(offset);
-        Z.sin_off = std::sin(offset);
-        for (int k = 0; k < Z.K; ++k) {
-            const int mm = m[s + k], nn = n[s + k], am = mm < 0 ? -mm : mm;
-            if (nn < am || ((nn - am) & 1)) return fail(PAOS_ERR_ARG, "invalid Zernike (m, n) = (%d, %d)", mm, nn);
-            const int kr = (nn - am) / 2;
-            Z.m[k] = mm;
-            Z.nn[k] = nn;
-            // scipy's eval_jacobi returns binom(k+alpha, k) * recurrence; (-1)^k from zernike.py:245-247
-            Z.coef[k] = coef[s + k] * binom(kr + am, kr) * ((kr & 1) ? -1.0 : 1.0);
-        }
-        cudaError_t e = launch_zernike(Z, screen, w->stream);
+        ZernParams Z;
+        if ((rc = fill_zern(w, Z, s, nterms, m, n, coef, nullptr, radius, dx, dy, offset, origin))) return rc;
+        cudaError_t e = launch_zernike(Z, dmask, screen, w->stream);
         if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "zernike launch failed: %s", cudaGetErrorString(e));
         w->stats.kernel_launches++;
     }
@@ -903,6 +925,43 @@ int paos_wfo_zernike(paos_wfo* w, int nterms, const int* m, const int* n, const 
         CU(cudaStreamSynchronize(w->stream));
     }
     return paos_wfo_phase_screen_device(w, screen, wl);
+}
+
+int paos_wfo_zernike(paos_wfo* w, int nterms, const int* m, const int* n, const double* coef, double radius, double dx,
+                     double dy, double offset, int origin, double wl, double* wfe_host_out) {
+    return paos_wfo_zernike_masked(w, nterms, m, n, coef, radius, dx, dy, offset, origin, wl, nullptr, wfe_host_out);
+}
+
+int paos_zernike_cov(paos_wfo* w, int nterms, const int* m, const int* n, const double* norm, double radius, double dx, double dy,
+                     double offset, int origin, const unsigned char* host_mask, double* cov_host_out) {
+    if (!w || !m || !n || !cov_host_out) return fail(PAOS_ERR_ARG, "null argument");
+    if (nterms < 1 || nterms > ZERN_MAX) return fail(PAOS_ERR_ARG, "covariance supports 1..%d polynomials", ZERN_MAX);
+    if (origin != 0 && origin != 1) return fail(PAOS_ERR_ARG, "origin must be 0 ('x') or 1 ('y')");
+    if (!(radius > 0.0)) return fail(PAOS_ERR_ARG, "radius must be positive");
+    int rc = set_device(w);
+    if (rc) return rc;
+    ZernParams Z;
+    if ((rc = fill_zern(w, Z, 0, nterms, m, n, nullptr, norm, radius, dx, dy, offset, origin))) return rc;
+    unsigned char* dmask;
+    if ((rc = upload_mask(w, host_mask, &dmask))) return rc;
+    const int K = nterms, per = K * K + 1;
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>(148 * 2, (size_t)w->n * w->n / per));
+    double* partial;
+    if ((rc = get_screen(w, &partial))) return rc;  // an n*n double buffer holds blocks * (K*K+1) partial sums
+    if ((size_t)blocks * per > (size_t)w->n * w->n) return fail(PAOS_ERR_UNSUPPORTED, "grid too small for %d covariance terms", K);
+    cudaError_t e = launch_zernike_cov(Z, dmask, partial, blocks, w->stream);
+    if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "covariance launch failed: %s", cudaGetErrorString(e));
+    w->stats.kernel_launches++;
+    std::vector<double> host((size_t)blocks * per);
+    CU(cudaMemcpyAsync(host.data(), partial, host.size() * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    std::vector<long double> sum(per, 0.0L);
+    for (int bk = 0; bk < blocks; ++bk)
+        for (int q = 0; q < per; ++q) sum[q] += host[(size_t)bk * per + q];
+    const long double count = sum[K * K];
+    if (!(count > 0)) return fail(PAOS_ERR_STATE, "every pixel is masked: the covariance is undefined");
+    for (int q = 0; q < K * K; ++q) cov_host_out[q] = (double)(sum[q] / count);  // np.ma.mean over the unmasked pixels
+    return PAOS_OK;
 }
 
 // run a private op list on the scratch field (PSD synthesis) without touching the handle's queue

@@ -120,12 +120,17 @@ class Sweep:
             s = k % nslots
             wfo, stream = self.wfos[s], self.streams[s]
             dst = out[k]
-            if native:
+            use_native = native
+            if use_native:
                 # whole chain planned and enqueued inside the library (paos_chain_run)
                 if not cache_compiled:
                     job.pop("_compiled", None)
-                cc = chain_mod.compile_job(job, psd_noise(job) if psd_noise is not None else None, device=self.device,
-                                           screen_cache=self._screens)
+                try:
+                    cc = chain_mod.compile_job(job, psd_noise(job) if psd_noise is not None else None, device=self.device,
+                                               screen_cache=self._screens)
+                except NotImplementedError:
+                    use_native = False  # e.g. orthonormal Zernikes, resampled grid sag: the Python driver handles them
+            if use_native:
                 if not cc.saved:
                     raise ValueError(f"job {job.get('tag', k)} saves no surface")
                 for idx in cc.saved:

@@ -356,28 +356,47 @@ class WFO:
         assert not np.any(np.diff(index) - 1), "Zernike sequence should be continuous"
         if origin not in ("x", "y"):
             raise ValueError(f"Origin {origin} not recognised. Origin shall be either x or y")
-        if orthonorm:
-            raise NotImplementedError("PolyOrthoNorm screens (zernike.py:388-402) are not on the device path yet")
-        if mask is not False and np.any(mask):
-            raise NotImplementedError("a pupil mask for Zernike screens is not on the device path yet")
         K = len(index)
         m, n = j2mn(K, ordering)
-        coef = np.ascontiguousarray(np.asarray(Z, dtype=np.float64) * zernike_norms(m, n, normalize))
-        if coef.shape != (K,):
+        norms = zernike_norms(m, n, normalize)
+        Z = np.asarray(Z, dtype=np.float64)
+        if Z.shape != (K,):
             raise ValueError("Z must have one coefficient per index")
         m32 = np.ascontiguousarray(m, dtype=np.int32)
         n32 = np.ascontiguousarray(n, dtype=np.int32)
+        pm, pn = m32.ctypes.data_as(C.POINTER(C.c_int)), n32.ctypes.data_as(C.POINTER(C.c_int))
+        mask_arr = None
+        if mask is not False and mask is not None and np.ndim(mask) > 0:
+            mask_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(mask, dtype=bool), (self._n, self._n)), dtype=np.uint8)
+        elif mask is True:
+            mask_arr = np.ones((self._n, self._n), dtype=np.uint8)
+        pmask = mask_arr.ctypes.data_as(C.c_void_p) if mask_arr is not None else None
+        off = float(np.deg2rad(offset))
+        org = 0 if origin == "x" else 1
+        if orthonorm:
+            # polynomials orthonormal on the pupil (zernike.py:388-402): covariance of the Zernikes over the unmasked
+            # pixels on the device, Cholesky / inverse of the K x K matrix on the host, and the screen is again a
+            # Zernike series with coefficients M^T Z (zernike.py:404-423)
+            nrm = np.ascontiguousarray(norms, dtype=np.float64)
+            cov = np.empty((K, K), dtype=np.float64)
+            check(lib.paos_zernike_cov(self._handle, K, pm, pn, nrm.ctypes.data_as(C.c_void_p), float(radius), float(self._dx),
+                                       float(self._dy), off, org, pmask, cov.ctypes.data_as(C.c_void_p)))
+            cov[np.abs(cov) < 1e-10] = 0.0
+            M = np.linalg.inv(np.linalg.cholesky(cov))
+            M[np.abs(M) < 1.0e-10] = 0.0
+            Z = M.T @ Z
+        coef = np.ascontiguousarray(Z * norms)
         wfe = np.empty((self._n, self._n), dtype=np.float64) if return_wfe else None
-        check(lib.paos_wfo_zernike(
-            self._handle, K, m32.ctypes.data_as(C.POINTER(C.c_int)), n32.ctypes.data_as(C.POINTER(C.c_int)),
-            coef.ctypes.data_as(C.POINTER(C.c_double)), float(radius), float(self._dx), float(self._dy),
-            float(np.deg2rad(offset)), 0 if origin == "x" else 1, float(self._wl),
-            wfe.ctypes.data_as(C.c_void_p) if return_wfe else None))
+        check(lib.paos_wfo_zernike_masked(
+            self._handle, K, pm, pn, coef.ctypes.data_as(C.POINTER(C.c_double)), float(radius), float(self._dx), float(self._dy),
+            off, org, float(self._wl), pmask, wfe.ctypes.data_as(C.c_void_p) if return_wfe else None))
         if not return_wfe:
             return None
         x = (np.arange(self._n) - self._n // 2) * self._dx
         y = (np.arange(self._n) - self._n // 2) * self._dy
         outside = np.sqrt(x[None, :] ** 2 + y[:, None] ** 2) / radius > 1.0
+        if mask_arr is not None:
+            outside = outside | mask_arr.astype(bool)
         return np.ma.MaskedArray(wfe, mask=outside, fill_value=0.0)
 
     def grid_sag(self, sag, nx, ny, delx, dely, xdec=0.0, ydec=0.0):

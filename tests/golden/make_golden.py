@@ -21,72 +21,19 @@ sys.path.insert(0, ROOT)
 from oracle import refload  # noqa: E402
 
 
-def field(n, seed):
-    rng = np.random.default_rng(seed)
-    return (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex128)
-
-
-def scalars(w):
-    return np.array([w.wl, w.z, w.w0, w.zw0, w.zr, w.dx, w.dy, w.C, w.fratio], dtype=np.float64)
-
-
 def primitives(ref):
-    n = 64
-    out = {}
-    w = ref.WFO(1.0, 3e-6, n, 4)
-    w._wfo = field(n, 1)
-    w.ptp(1234.5)
-    out["ptp"] = w._wfo.copy()
-    out["ptp_s"] = scalars(w)
-    w.wts(2.0e6)
-    out["wts"] = w._wfo.copy()
-    out["wts_s"] = scalars(w)
-    w.stw(-1.5e6)
-    out["stw"] = w._wfo.copy()
-    out["stw_s"] = scalars(w)
+    """The shared scenario script (tests/golden_cases.py) driven with the unmodified reference WFO."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import golden_cases
 
-    w = ref.WFO(1.0, 3e-6, n, 4)
-    w.aperture(0.0, 0.0, r=0.5, shape="circular")
-    w.make_stop()
-    out["stop"] = w._wfo.copy()
-    w.lens(1.0)
-    out["lens"] = w._wfo.copy()
-    out["lens_s"] = scalars(w)
-    w.propagate(1.0)
-    out["prop_OI"] = w._wfo.copy()
-    out["prop_OI_s"] = scalars(w)
-    w.propagate(0.5)
-    out["prop_next"] = w._wfo.copy()
-    out["prop_next_s"] = scalars(w)
-    out["prop_next_name"] = np.array(w.propagator)
+    def setf(w, a):
+        w._wfo = a.copy()
 
-    w = ref.WFO(1.0, 1e-6, n, 2)
-    w.aperture(0.013, -0.021, hx=0.5, hy=0.37, shape="elliptical")
-    w.aperture(0.1003, 0.0, hx=0.0213, hy=0.9, shape="rectangular", obscuration=True)
-    out["masks"] = w._wfo.copy()
+    def psd(w, noise, **kw):
+        np.random.seed(11)  # the reference draws from the global numpy state (psd.py:113,:142)
+        return w.psd(units=ref.units.nm, **kw)
 
-    rng = np.random.default_rng(3)
-    Z = rng.standard_normal(36) * 50e-9
-    out["zern_Z"] = Z
-    for ordering in ("ansi", "standard", "noll", "fringe"):
-        w = ref.WFO(1.0, 1e-6, n, 2)
-        wfe = w.zernikes(np.arange(36), Z, ordering, True, 0.5, origin="x")
-        out[f"zern_{ordering}_wfe"] = wfe.filled(0)
-        out[f"zern_{ordering}_mask"] = np.ma.getmaskarray(wfe)
-        out[f"zern_{ordering}_wfo"] = w._wfo.copy()
-    w = ref.WFO(1.0, 1e-6, n, 2)
-    wfe = w.zernikes(np.arange(11), Z[:11], "noll", False, 0.45, offset=33.0, origin="y")
-    out["zern_y_wfe"] = wfe.filled(0)
-    out["zern_y_wfo"] = w._wfo.copy()
-
-    n = 256
-    w = ref.WFO(1.0, 1e-6, n, 2)
-    np.random.seed(11)  # the reference draws from the global numpy state (psd.py:113,:142)
-    wfe = w.psd(A=221.0, B=0.0, C=1.5, fknee=1.0, fmin=5.0, fmax=60.0, SR=2.0, units=ref.units.nm)
-    out["psd_wfe"] = np.asarray(wfe)[96:160, 96:160].copy()
-    out["psd_wfo"] = w._wfo[96:160, 96:160].copy()
-    out["psd_sum"] = np.array([np.sum(np.asarray(wfe)), np.sum(np.asarray(wfe) ** 2)])
-    return out
+    return golden_cases.primitives(ref.WFO, setf, lambda w: w._wfo.copy(), psd)
 
 
 def crop(a, k=64):

@@ -54,6 +54,16 @@ def primitives(make, set_field, get_field, psd_call):
     wfe = w.zernikes(np.arange(11), Z[:11], "noll", False, 0.45, offset=33.0, origin="y")
     out["zern_y_wfe"], out["zern_y_wfo"] = wfe.filled(0), get_field(w)
 
+    # pupil mask + polynomials orthonormalised on it (zernike.py:388-402), elliptical pupil inside the unit disc
+    w = make(1.0, 1e-6, n, 2)
+    x = (np.arange(n) - n // 2) * w.dx
+    pupil_mask = (x[None, :] / 0.42) ** 2 + (x[:, None] / 0.3) ** 2 > 1.0
+    wfe = w.zernikes(np.arange(15), Z[:15], "noll", True, 0.5, origin="x", orthonorm=True, mask=pupil_mask)
+    out["zern_ortho_wfe"], out["zern_ortho_mask"], out["zern_ortho_wfo"] = wfe.filled(0), np.ma.getmaskarray(wfe), get_field(w)
+    w = make(1.0, 1e-6, n, 2)
+    wfe = w.zernikes(np.arange(15), Z[:15], "ansi", False, 0.5, origin="y", mask=pupil_mask)
+    out["zern_masked_wfe"], out["zern_masked_mask"], out["zern_masked_wfo"] = wfe.filled(0), np.ma.getmaskarray(wfe), get_field(w)
+
     n = 256
     w = make(1.0, 1e-6, n, 2)
     rs = np.random.RandomState(11)

@@ -177,3 +177,29 @@ def test_native_chain_runner_matches_python_driver(which, tmp_path):
             a, b = meta_n[k][key], meta_p[k][key]
             assert a == b or abs(a - b) <= 1e-13 * abs(b), (which, key, a, b)
         assert meta_n[k]["propagator"] == meta_p[k]["propagator"]
+
+
+def test_hand_built_chain_with_orthonormal_zernikes():
+    """A hand-built opt_chain (legal input of run, cf. notebook/ValidateThicklens.ipynb) whose Zernike surface is
+    orthonormalised on its elliptical pupil (run.py:134-152, zernike.py:388-402)."""
+    import paos_b200
+
+    def surf(num, kind, thickness=0.0, curvature=0.0, **extra):
+        d = dict(num=num, type=kind, name=f"S{num}", is_stop=False, save=True, R=np.nan, T=thickness, material=None,
+                 ABCDt=paos_b200.ABCD(thickness, curvature), ABCDs=paos_b200.ABCD(thickness, curvature))
+        d.update(extra)
+        return d
+
+    rng = np.random.default_rng(5)
+    chain = {
+        2: surf(2, "Standard", is_stop=True, aperture=dict(shape="elliptical", type="aperture", xrad=0.5, yrad=0.4, xc=np.nan, yc=np.nan)),
+        3: surf(3, "Zernike", Zindex=np.arange(21), Z=rng.standard_normal(21) * 40e-9, Zordering="standard", Znormalize=True,
+                Zradius=0.5, Zorigin="x", Zorthonorm=True,
+                aperture=dict(shape="elliptical", type="aperture", xrad=0.45, yrad=0.35, xc=0.01, yc=-0.02)),
+        4: surf(4, "Paraxial Lens", thickness=8.0, curvature=1 / 8.0),
+        5: surf(5, "Standard"),
+    }
+    job = dict(pupil_diameter=1.0, wavelength=1.5e-6, gridsize=256, zoom=4, field={"us": 0.0, "ut": 0.0}, opt_chain=chain)
+    got, ref = both(job)
+    assert sorted(ref) == [2, 3, 4, 5] and ref[3]["wfe"] is not None
+    compare(got, ref, TOL["complex128"])
