@@ -244,6 +244,15 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
                 }
             }
         }
+        if (P.genmask >> pos & 1) {
+            // A mask often blanks whole lines (everything outside the aperture's shadow: 3/4 of the lines of a pupil
+            // plane at zoom 4).  Every later operation of the pass is multiplicative or a line FFT, so an all-zero
+            // tile stays exactly zero: skip straight to the store.  (CTA-uniform: the barrier-or covers all W lines.)
+            bool nz = false;
+#pragma unroll
+            for (int j = 0; j < E; ++j) nz |= (v[j].x != (R)0) | (v[j].y != (R)0);
+            if (!__syncthreads_or(nz)) break;
+        }
         const C<R>* tab = reinterpret_cast<const C<R>*>(P.tab[pos]);
         if (tab) {
 #pragma unroll
