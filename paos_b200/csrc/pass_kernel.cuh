@@ -168,8 +168,25 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
     const C<R>* src = reinterpret_cast<const C<R>*>(P.src);
     C<R>* dst = reinterpret_cast<C<R>*>(P.dst);
 
+    // An elliptical *aperture* anywhere in this pass blanks every line that misses its bounding box (same FP32 test
+    // and margins as the per-pixel classification below): such a tile is zero at the end of the pass whatever
+    // happens before the mask, so neither its load nor any of its transforms is needed.
+    bool blank = false;
+    if (P.genmask) {
+        for (int gi = 0; gi < P.ngen; ++gi) {
+            const GenOp& g = P.gen[gi];
+            if (g.kind != GEN_ELLIPSE || g.flag) continue;
+            const float bq = COL ? ((float)line - (float)g.p0) * (float)g.p2 : ((float)line - (float)g.p1) * (float)g.p3;
+            if (bq * bq >= (float)g.p6 + 1e-5f) blank = true;
+        }
+        blank = __syncthreads_and(blank) != 0;  // CTA-uniform: all W lines of the tile
+    }
+
     C<R> v[E];
-    if (src) {
+    if (blank) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) v[j] = C<R>((R)0, (R)0);
+    } else if (src) {
 #pragma unroll
         for (int j = 0; j < E; ++j) {
             const int idx = t + j * T;
@@ -186,7 +203,7 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
 #pragma unroll
         for (int j = 0; j < E; ++j) v[j] = v[j] * c;
     }
-    for (int pos = 0;; ++pos) {
+    for (int pos = 0; !blank; ++pos) {
         // diagonal factors of this position: general (masks, screens, stop scalar), then the along-line table
         if (P.genmask >> pos & 1) {
             for (int gi = 0; gi < P.ngen; ++gi) {
