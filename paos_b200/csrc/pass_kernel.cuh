@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
         for (int j = 0; j < E; ++j) {
             const int idx = t + j * T;
             const size_t ga = COL ? ((size_t)idx * N + line) : ((size_t)line * N + idx);
-            out[ga] = readout_value<R>(v[j], P.readout);
+            // |.|^2 inline (the common sweep read-out); |.| and angle go through the out-of-line libm path
+            out[ga] = (P.readout == 3) ? v[j].x * v[j].x + v[j].y * v[j].y : readout_value<R>(v[j], P.readout);
         }
     }
 }

@@ -315,7 +315,8 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
     split_ops(w, ops, th[0], th[1], gens);
     size_t cur[2] = {0, 0};
     bool have_src = w->materialized;
-    int axis = 0;
+    static const int start_axis = getenv("PAOS_START_AXIS") ? atoi(getenv("PAOS_START_AXIS")) : 0;
+    int axis = start_axis;
     int idle = 0;
     while (cur[0] < th[0].size() || cur[1] < th[1].size()) {
         std::vector<Item>& mine = th[axis];
