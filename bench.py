@@ -329,7 +329,8 @@ def run_ours(args):
                     "sweep_GBps": actual, "sweep_frac": actual / peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                     "note": "achieved counts 32*N^2 B per line-FFT sweep (SURVEY 8d: 64*N^2 per FFT2); a pass chains several "
-                            "line FFTs per sweep, so achieved may exceed peak; sweep_GBps = real read+write bytes of the field / time"}
+                            "line FFTs per sweep and lines blanked by an aperture mask are neither loaded nor transformed, so achieved exceeds "
+                            "the HBM peak; sweep_GBps = upper bound of the real read+write bytes of the field / time"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------------
     cpu = None
