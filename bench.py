@@ -268,6 +268,7 @@ def run_ours(args):
     # ---- final gather of the PSF stack (the single collective; outside the per-step timing) -------
     gather_ms = None
     if world > 1:
+        sweep_mod.gather_stack(stack[:1], [1] * world, dst=0)  # first use builds NCCL's point-to-point connections
         torch.cuda.synchronize()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()

@@ -223,8 +223,13 @@ def gather_stack(local, counts, dst=0, group=None):
         pad[: local.shape[0]] = local
     pad = pad.contiguous()
     if rank == dst:
-        bufs = [torch.empty_like(pad) for _ in range(world)]
+        # receive straight into one [world * width, N, N] stack (views as the gather list): no second copy when the
+        # blocks are equal, which is the common case
+        full = torch.empty((world * width,) + tuple(pad.shape[1:]), dtype=pad.dtype, device=pad.device)
+        bufs = [full[r * width:(r + 1) * width] for r in range(world)]
         dist.gather(pad, gather_list=bufs, dst=dst, group=group)
+        if all(c == width for c in counts):
+            return full
         return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
     dist.gather(pad, gather_list=None, dst=dst, group=group)
     return None

@@ -107,3 +107,19 @@ def test_headline_chain_2048_against_oracle():
     # and in the stated single-precision mode
     got32 = paos_b200.run(*args, keys=("amplitude",), dtype="complex64")
     assert relerr(got32[max(got32)]["amplitude"], ref_amp) <= TOL["complex64"]
+
+
+def test_grid_sag_chain_4096_against_oracle(tmp_path):
+    """BASELINE config 5 at its full size: test_Grid_Sag.ini at 4096^2 complex128 with the synthetic on-grid sag."""
+    import paos_b200
+    from oracle import paos_np
+    from paos_b200 import configs
+
+    job = configs.grid_sag(grid=4096, wavelengths=(3.0,), workdir=str(tmp_path))[0]
+    args = (job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"], job["opt_chain"])
+    ref = paos_np.run(*args)
+    got = paos_b200.run(*args, keys=("amplitude",))
+    assert sorted(got) == sorted(ref)
+    for num in ref:
+        assert relerr(got[num]["amplitude"], ref[num]["amplitude"]) <= TOL["complex128"], num
+        assert got[num]["dx"] == ref[num]["dx"]
