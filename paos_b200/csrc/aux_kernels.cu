@@ -107,14 +107,25 @@ struct Norm2Params {
 template <typename R>
 __global__ void __launch_bounds__(256) norm2_partial_kernel(const __grid_constant__ Norm2Params P, double* __restrict__ partials) {
     const int n = P.n;
-    const size_t total = (size_t)n * n;
     const C<R>* src = reinterpret_cast<const C<R>*>(P.src);
     double acc = 0.0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int iy = (int)(i / n), ix = (int)(i % n);
-        C<R> v = src ? ldc(src + i) : C<R>((R)1, (R)0);
-        for (int g = 0; g < P.ngen; ++g) apply_gen(v, P.gen[g], ix, iy, n);
-        acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+    // one row per CTA step (32-bit index math; the 64-bit div/mod of a flat index cost more than the mask itself)
+    for (int iy = blockIdx.x; iy < n; iy += gridDim.x) {
+        // a row that misses the bounding box of an elliptical aperture contributes nothing
+        bool blank = false;
+        for (int g = 0; g < P.ngen; ++g) {
+            const GenOp& gg = P.gen[g];
+            if (gg.kind == GEN_ELLIPSE && !gg.flag) {
+                const float bq = ((float)iy - (float)gg.p1) * (float)gg.p3;
+                if (bq * bq >= (float)gg.p6 + 1e-5f) blank = true;
+            }
+        }
+        if (blank) continue;
+        for (int ix = threadIdx.x; ix < n; ix += blockDim.x) {
+            C<R> v = src ? ldc(src + (size_t)iy * n + ix) : C<R>((R)1, (R)0);
+            for (int g = 0; g < P.ngen; ++g) apply_gen(v, P.gen[g], ix, iy, n);
+            acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+        }
     }
     __shared__ double red[256];
     red[threadIdx.x] = acc;
