@@ -42,6 +42,7 @@ struct PassParams {
     const void* ctab_out;      // same, applied after the last position
     unsigned genmask;          // bit p set: some general factor sits at position p
     unsigned sgnmask;          // bit p set: position p carries the sign (-1)^index (no table)
+    int tile_lo, tile_hi;      // tiles outside this range are blanked by an aperture of this pass: store zeros only
     int readout;               // 0: store the complex field; PAOS_READ_* (1..3): store a real read-out into dst_real instead
     int pad;
     void* dst_real;

@@ -4,6 +4,16 @@
 
 namespace paosb {
 
+//                 N    E  Wrow Wcol minb(row) minb(col)
+#define PAOS_TILE_TABLE \
+    PAOS_CASE(64, 8, 16, 16, 1, 1) \
+    PAOS_CASE(128, 8, 8, 8, 1, 1) \
+    PAOS_CASE(256, 16, 4, 4, 2, 2) \
+    PAOS_CASE(512, 8, 2, 2, 4, 4) \
+    PAOS_CASE(1024, 16, 2, 4, 4, 2) \
+    PAOS_CASE(2048, 16, 1, 2, 4, 2) \
+    PAOS_CASE(4096, 16, 1, 2, 2, 1)
+
 #define PAOS_CASE(N, E, WR, WC, MR, MC)                                                              \
     case N:                                                                                          \
         return col ? launch_pass_t<double, N, E, WC, true, MC>(P, tw1, tw2, st, device)                 \
@@ -12,15 +22,19 @@ namespace paosb {
 cudaError_t launch_pass_c128(int n, bool col, const PassParams& P, const void* tw1, const void* tw2,
                              cudaStream_t st, int device) {
     switch (n) {
-        //        N    E  Wrow Wcol minb
-        PAOS_CASE(64, 8, 16, 16, 1, 1)
-        PAOS_CASE(128, 8, 8, 8, 1, 1)
-        PAOS_CASE(256, 16, 4, 4, 2, 2)
-        PAOS_CASE(512, 8, 2, 2, 4, 4)
-        PAOS_CASE(1024, 16, 2, 4, 4, 2)
-        PAOS_CASE(2048, 16, 1, 2, 4, 2)
-        PAOS_CASE(4096, 16, 1, 2, 2, 1)
+        PAOS_TILE_TABLE
         default: return cudaErrorInvalidValue;
+    }
+}
+#undef PAOS_CASE
+
+#define PAOS_CASE(N, E, WR, WC, MR, MC) \
+    case N:                             \
+        return col ? WC : WR;
+int tile_width_c128(int n, bool col) {
+    switch (n) {
+        PAOS_TILE_TABLE
+        default: return 1;
     }
 }
 #undef PAOS_CASE

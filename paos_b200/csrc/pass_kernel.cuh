@@ -150,6 +150,25 @@ __device__ __forceinline__ void apply_gen(C<R>& v, const GenOp& g, int ix, int i
 
 // ---- the pass kernel ---------------------------------------------------------------------------------
 // R: real type; N: line length; E: points per thread; W: lines per CTA; COL: lines are columns.
+// zero store of one tile (and of its read-out); out of line so that it does not share registers with the main path
+template <typename R, int N, int E, int W, bool COL>
+__device__ __noinline__ void store_zero_tile(const PassParams& P) {
+    constexpr int T = N / E;
+    const int tid = threadIdx.x;
+    const int w = COL ? (tid % W) : (tid / T);
+    const int t = COL ? (tid / W) : (tid % T);
+    const int line = blockIdx.x * W + w;
+    C<R>* dst = reinterpret_cast<C<R>*>(P.dst);
+    R* out = reinterpret_cast<R*>(P.dst_real);
+    const C<R> zero((R)0, (R)0);
+    for (int j = 0; j < E; ++j) {
+        const int idx = t + j * T;
+        const size_t ga = COL ? ((size_t)idx * N + line) : ((size_t)line * N + idx);
+        stc_stream(dst + ga, zero);
+        if (P.readout) out[ga] = (R)0;  // |0|, angle(0), |0|^2
+    }
+}
+
 template <typename R, int N, int E, int W, bool COL, int MINB>
 __global__ void __launch_bounds__(W*(N / E), MINB)
     pass_kernel(const __grid_constant__ PassParams P, const C<R>* __restrict__ tw1, const C<R>* __restrict__ tw2) {
@@ -168,25 +187,16 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
     const C<R>* src = reinterpret_cast<const C<R>*>(P.src);
     C<R>* dst = reinterpret_cast<C<R>*>(P.dst);
 
-    // An elliptical *aperture* anywhere in this pass blanks every line that misses its bounding box (same FP32 test
-    // and margins as the per-pixel classification below): such a tile is zero at the end of the pass whatever
-    // happens before the mask, so neither its load nor any of its transforms is needed.
-    bool blank = false;
-    if (P.genmask) {
-        for (int gi = 0; gi < P.ngen; ++gi) {
-            const GenOp& g = P.gen[gi];
-            if (g.kind != GEN_ELLIPSE || g.flag) continue;
-            const float bq = COL ? ((float)line - (float)g.p0) * (float)g.p2 : ((float)line - (float)g.p1) * (float)g.p3;
-            if (bq * bq >= (float)g.p6 + 1e-5f) blank = true;
-        }
-        blank = __syncthreads_and(blank) != 0;  // CTA-uniform: all W lines of the tile
+    // Tiles outside [tile_lo, tile_hi] are blanked by an elliptical aperture somewhere in this pass (the planner
+    // works the range out from the apertures' bounding boxes): such a tile is zero at the end of the pass whatever
+    // happens before the mask, so it is neither loaded nor transformed, only stored as zeros.
+    if ((int)blockIdx.x < P.tile_lo || (int)blockIdx.x > P.tile_hi) {
+        store_zero_tile<R, N, E, W, COL>(P);
+        return;
     }
 
     C<R> v[E];
-    if (blank) {
-#pragma unroll
-        for (int j = 0; j < E; ++j) v[j] = C<R>((R)0, (R)0);
-    } else if (src) {
+    if (src) {
 #pragma unroll
         for (int j = 0; j < E; ++j) {
             const int idx = t + j * T;
@@ -203,7 +213,7 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
 #pragma unroll
         for (int j = 0; j < E; ++j) v[j] = v[j] * c;
     }
-    for (int pos = 0; !blank; ++pos) {
+    for (int pos = 0;; ++pos) {
         // diagonal factors of this position: general (masks, screens, stop scalar), then the along-line table
         if (P.genmask >> pos & 1) {
             for (int gi = 0; gi < P.ngen; ++gi) {
@@ -260,15 +270,6 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
                     }
                 }
             }
-        }
-        if (P.genmask >> pos & 1) {
-            // A mask often blanks whole lines (everything outside the aperture's shadow: 3/4 of the lines of a pupil
-            // plane at zoom 4).  Every later operation of the pass is multiplicative or a line FFT, so an all-zero
-            // tile stays exactly zero: skip straight to the store.  (CTA-uniform: the barrier-or covers all W lines.)
-            bool nz = false;
-#pragma unroll
-            for (int j = 0; j < E; ++j) nz |= (v[j].x != (R)0) | (v[j].y != (R)0);
-            if (!__syncthreads_or(nz)) break;
         }
         const C<R>* tab = reinterpret_cast<const C<R>*>(P.tab[pos]);
         if (tab) {
@@ -335,6 +336,7 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
         for (int j = 0; j < E; ++j) {
             const int idx = t + j * T;
             const size_t ga = COL ? ((size_t)idx * N + line) : ((size_t)line * N + idx);
+            // |.|^2 inline (the common sweep read-out); |.| and angle go through the out-of-line libm path
             // |.|^2 inline (the common sweep read-out); |.| and angle go through the out-of-line libm path
             out[ga] = (P.readout == 3) ? v[j].x * v[j].x + v[j].y * v[j].y : readout_value<R>(v[j], P.readout);
         }

@@ -380,6 +380,26 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
                 }
             }
         }
+        // lines that miss the bounding box of an elliptical *aperture* of this pass end up exactly zero: a pixel whose
+        // centre lies at normalised distance >= 1 + d from the centre (d = half the pixel diagonal in the frame where
+        // the ellipse is the unit circle, sqrt(p6) = 1 + d) is entirely outside, and every pixel of such a line is
+        int line_lo = 0, line_hi = w->n - 1;
+        for (int gi = 0; gi < P.ngen; ++gi) {
+            const GenOp& g = P.gen[gi];
+            if (g.kind != GEN_ELLIPSE || g.flag) continue;
+            const double c0 = axis == 1 ? g.p0 : g.p1, s = axis == 1 ? g.p2 : g.p3;  // column pass: line = ix
+            const double reach = (std::sqrt(g.p6) + 1e-9) / s;
+            if (!std::isfinite(reach) || !std::isfinite(c0)) continue;
+            line_lo = std::max(line_lo, (int)std::ceil(c0 - reach));
+            line_hi = std::min(line_hi, (int)std::floor(c0 + reach));
+        }
+        P.tile_lo = 0;
+        P.tile_hi = 0x7fffffff;
+        if (line_lo > 0 || line_hi < w->n - 1) {
+            const int W = tile_width(w->n, w->dtype, axis == 1);
+            P.tile_lo = line_lo / W;
+            P.tile_hi = line_hi >= line_lo ? line_hi / W : -1;  // empty range: everything is blank
+        }
         for (int p = 0; p <= P.nfft; ++p) {
             P.scl[p] = 1.0;
             P.tab[p] = nullptr;
@@ -404,6 +424,7 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
         P.src = w->materialized ? field : nullptr;
         P.dst = field;
         P.scl[0] = 1.0;
+        P.tile_hi = 0x7fffffff;
         PlannedPass pp;
         pp.col = false;
         pp.P = P;
