@@ -144,15 +144,14 @@ class CompiledChain:
 
 
 def _on_grid_sag(item, n, pupil_diameter, zoom):
-    """Screen (metres, 0 where masked) of a Grid Sag surface that already sits on the WFO grid at INIT sampling;
-    the general case goes through ``WFO.grid_sag`` in the Python driver."""
-    sag = item["grid_sag"]
-    if not isinstance(sag, np.ma.MaskedArray):
-        sag = np.ma.MaskedArray(sag, mask=~np.isfinite(sag) | (sag == 0))
+    """Screen (metres, 0 where masked) of a Grid Sag surface at INIT sampling (``paos_b200/sag.py``); the native runner
+    takes surfaces that precede any change of sampling, which is where lens files put them."""
+    from .sag import prepare_sag
+
     d = pupil_diameter * zoom / n
-    if not (sag.shape == (n, n) and item["xdec"] == 0 and item["ydec"] == 0 and item["delx"] == d and item["dely"] == d):
-        raise NotImplementedError("the native chain runner takes grid-sag maps that are already on the WFO grid")
-    return np.ascontiguousarray(sag.filled(0.0), dtype=np.float64)
+    screen, _ = prepare_sag(item["grid_sag"], int(item["nx"]), int(item["ny"]), item["delx"], item["dely"], item["xdec"],
+                            item["ydec"], n, d, d)
+    return screen
 
 
 def compile_job(job, psd_noise=None, device=None, screen_cache=None):

@@ -57,18 +57,6 @@ template <> __device__ __forceinline__ C<float> ldc_stream<float>(const C<float>
     asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "l"(p));
     return C<float>(x, y);
 }
-// read-only table that is used once per CTA: keep it out of L1 so that the twiddles stay resident
-template <typename R> __device__ __forceinline__ C<R> ldc_once(const C<R>* p);
-template <> __device__ __forceinline__ C<double> ldc_once<double>(const C<double>* p) {
-    double x, y;
-    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p));
-    return C<double>(x, y);
-}
-template <> __device__ __forceinline__ C<float> ldc_once<float>(const C<float>* p) {
-    float x, y;
-    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "l"(p));
-    return C<float>(x, y);
-}
 template <typename R> __device__ __forceinline__ void stc_stream(C<R>* p, C<R> a) {
     typedef typename cx2<R>::type V;
     V v;

@@ -315,8 +315,7 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
     split_ops(w, ops, th[0], th[1], gens);
     size_t cur[2] = {0, 0};
     bool have_src = w->materialized;
-    static const int start_axis = getenv("PAOS_START_AXIS") ? atoi(getenv("PAOS_START_AXIS")) : 0;
-    int axis = start_axis;
+    int axis = 0;
     int idle = 0;
     while (cur[0] < th[0].size() || cur[1] < th[1].size()) {
         std::vector<Item>& mine = th[axis];
@@ -429,12 +428,6 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
         pp.col = false;
         pp.P = P;
         plan.passes.push_back(pp);
-    }
-    // timing experiments only (results are wrong): drop the general factors / the phase tables from every pass
-    static const bool exp_nogen = getenv("PAOS_EXP_SKIP_GENS") != nullptr, exp_notab = getenv("PAOS_EXP_SKIP_TABLES") != nullptr;
-    for (PlannedPass& pp : plan.passes) {
-        if (exp_nogen) { pp.P.ngen = 0; pp.P.genmask = 0; }
-        if (exp_notab) for (int p2 = 0; p2 <= KMAX; ++p2) pp.P.tab[p2] = nullptr;
     }
     static const bool debug_plan = getenv("PAOS_DEBUG_PLAN") != nullptr;
     if (debug_plan) {

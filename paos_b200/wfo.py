@@ -9,7 +9,6 @@ and executed when something is read, so a chain of surfaces costs a handful of s
 There is no CPU path: constructing a ``WFO`` without a usable B200 raises ``PaosCudaError``.
 """
 import ctypes as C
-import math
 
 import numpy as np
 
@@ -400,26 +399,14 @@ class WFO:
         return np.ma.MaskedArray(wfe, mask=outside, fill_value=0.0)
 
     def grid_sag(self, sag, nx, ny, delx, dely, xdec=0.0, ydec=0.0):
-        """Grid-sag phase screen (``wfo.py:656-871``) for a map that already sits on the WFO grid; the
-        resampling branch (skimage in the reference) is not on the device path yet."""
-        assert sag.ndim == 2, "sag shall be a 2D array"
-        if not isinstance(sag, np.ma.MaskedArray):
-            sag = np.ma.MaskedArray(sag, mask=~np.isfinite(sag) | (sag == 0))
-        mask = np.ma.getmaskarray(sag).astype(float)
-        data = sag.filled(0.0)
-        n = self._n
-        on_grid = (
-            xdec == 0 and ydec == 0 and data.shape == (n, n)
-            and int(np.floor((data.shape[1] * delx - n * self._dx) / delx)) == 0
-            and int(np.floor((data.shape[0] * dely - n * self._dy) / dely)) == 0
-            and delx / self._dx == 1 and dely / self._dy == 1
-        )
-        if not on_grid:
-            raise NotImplementedError("grid_sag resampling is not implemented: supply the sag on the WFO grid")
-        out = np.ma.MaskedArray(data, mask=mask > 0.1)
-        screen = np.ascontiguousarray(out.filled(0), dtype=np.float64)
+        """Grid-sag phase screen (``wfo.py:656-871``).  The map is masked, recentred and padded / cropped on the host
+        (``paos_b200/sag.py``, input preparation as in the reference); the phase multiply runs in the fused passes.
+        Maps that would need the reference's skimage resampling raise ``NotImplementedError``."""
+        from .sag import prepare_sag
+
+        screen, mask = prepare_sag(sag, int(nx), int(ny), delx, dely, xdec, ydec, self._n, self._dx, self._dy)
         check(lib.paos_wfo_phase_screen(self._handle, screen.ctypes.data_as(C.c_void_p), float(self._wl)))
-        return out
+        return np.ma.MaskedArray(np.where(mask, 0.0, screen), mask=mask)
 
     def psd(self, A=10.0, B=0.0, C=0.0, fknee=1.0, fmin=None, fmax=None, SR=0.0, units=None, noise=None,
             seed=None, return_wfe=True):

@@ -64,6 +64,15 @@ def primitives(make, set_field, get_field, psd_call):
     wfe = w.zernikes(np.arange(15), Z[:15], "ansi", False, 0.5, origin="y", mask=pupil_mask)
     out["zern_masked_wfe"], out["zern_masked_mask"], out["zern_masked_wfo"] = wfe.filled(0), np.ma.getmaskarray(wfe), get_field(w)
 
+    # grid sag: masked pixels (zeros, NaN), smaller than the grid in y and larger in x (pad + crop), decentred
+    w = make(1.0, 1e-6, n, 2)
+    rs2 = np.random.RandomState(5)
+    sag = rs2.randn(56, 72) * 30e-9
+    sag[:3, :] = 0.0
+    sag[5, 7] = np.nan
+    res = w.grid_sag(sag, 72, 56, w.dx, w.dy, 1.3, -2.6)
+    out["sag_wfe"], out["sag_mask"], out["sag_wfo"] = res.filled(0), np.ma.getmaskarray(res), get_field(w)
+
     n = 256
     w = make(1.0, 1e-6, n, 2)
     rs = np.random.RandomState(11)

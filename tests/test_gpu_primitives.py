@@ -237,3 +237,26 @@ def test_reads_after_chain_do_not_disturb_state():
     assert relerr(p.d.psf, p.o.amplitude**2) <= 1e-12
     p.call("propagate", 2.0)
     p.check()
+
+
+@pytest.mark.parametrize("ny,nx,xdec,ydec", [(128, 128, 0.0, 0.0), (96, 80, 0.0, 0.0), (160, 192, 0.0, 0.0), (112, 144, 1.3, -2.6)])
+def test_grid_sag_pad_crop_decentre(ny, nx, xdec, ydec):
+    n = 128
+    rng = np.random.default_rng(9)
+    sag = rng.standard_normal((ny, nx)) * 30e-9
+    sag[:4, :] = 0.0
+    sag[7, 9] = np.nan
+    p = Pair(1.0, 1e-6, n, 2)
+    d = p.d.dx
+    ro, rd = p.call("grid_sag", sag, nx, ny, d, d, xdec, ydec)
+    assert np.array_equal(ro.mask, rd.mask)
+    assert relerr(rd.filled(0), ro.filled(0)) <= 1e-13
+    p.check()
+
+
+def test_grid_sag_needing_resampling_is_refused():
+    import paos_b200
+
+    w = paos_b200.WFO(1.0, 1e-6, 128, 2)
+    with pytest.raises(NotImplementedError):
+        w.grid_sag(np.ones((128, 128)) * 1e-9, 128, 128, 0.7 * w.dx, 0.7 * w.dy)

@@ -118,3 +118,19 @@ def test_parse_config_equals_reference(name, data_dir):
                     assert np.array_equal(va, vb)
                 else:
                     assert va == vb or (isinstance(va, float) and np.isnan(va) and np.isnan(vb))
+
+
+@needs_reference
+@pytest.mark.parametrize("ny,nx,xdec,ydec", [(64, 64, 0.0, 0.0), (48, 40, 0.0, 0.0), (80, 96, 0.0, 0.0), (56, 72, 1.3, -2.6)])
+def test_grid_sag_pad_crop_decentre_equals_reference(ny, nx, xdec, ydec):
+    """Masking, Fourier recentring and pad / crop of a grid-sag map (wfo.py:753-845) against the unmodified reference
+    (its skimage calls are stubbed to raise, so reaching them would fail the test)."""
+    ref = refload.load()
+    rng = np.random.default_rng(0)
+    sag = rng.standard_normal((ny, nx)) * 30e-9
+    sag[:3, :] = 0.0
+    sag[5, 7] = np.nan
+    a, b = ref.WFO(1.0, 1e-6, 64, 2), paos_np.WFO(1.0, 1e-6, 64, 2)
+    ra = a.grid_sag(sag.copy(), nx, ny, a.dx, a.dy, xdec, ydec)
+    rb = b.grid_sag(sag.copy(), nx, ny, b.dx, b.dy, xdec, ydec)
+    assert np.array_equal(a._wfo, b._wfo) and np.array_equal(ra.filled(0), rb.filled(0)) and np.array_equal(ra.mask, rb.mask)
