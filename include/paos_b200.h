@@ -93,7 +93,8 @@ int paos_wfo_upload_device(paos_wfo *w, const void *dev_src);
 /* wfo.py:203-278 (aperture): multiply by the mask (or 1-mask when obscuration != 0).  All lengths in
  * pixels as the reference passes them to photutils: centre (ixc, iyc) = (xc/dx + N/2, yc/dy + N/2);
  * ellipse: semi-axes (ihx, ihy), exact pixel/ellipse overlap; rectangle: full sides (ihx, ihy), 32x32
- * sub-pixel sampling.  theta in radians; only theta == 0 is implemented (run.py:114-121 never tilts). */
+ * sub-pixel sampling.  theta in radians, counter-clockwise from +x (photutils convention); run.py:114-121 never
+ * tilts, so theta != 0 takes a slower per-pixel path. */
 int paos_wfo_aperture(paos_wfo *w, int shape, double ixc, double iyc, double ihx, double ihy,
                       double theta, int obscuration);
 /* wfo.py:195-201 (make_stop): divide by sqrt(sum |wfo|^2) */

@@ -17,7 +17,9 @@ enum GenKind : int {
     GEN_RECT = 2,       // 32x32 sub-pixel rectangle: ptr0 = x counts, ptr1 = y counts (double[N])
     GEN_SCREEN = 3,     // exp(i*(2*pi*w)/wl): ptr0 = w (double[N*N]), p0 = wl
     GEN_SCALE_DEV = 4,  // multiply by *ptr0 (double in device memory)
-    GEN_PSD = 5         // PSD amplitude filter in frequency space (psd.py:121-129), see aux_kernels.cu
+    GEN_PSD = 5,        // PSD amplitude filter in frequency space (psd.py:121-129), see aux_kernels.cu
+    GEN_ELLIPSE_TILT = 6,  // tilted ellipse: p0..p6 as GEN_ELLIPSE, p7 = cos(theta), p8 = sin(theta)
+    GEN_RECT_TILT = 7      // tilted rectangle, 32x32 sub-pixel count per pixel: p0=xc p1=yc p2=w/2 p3=h/2 p7=cos p8=sin
 };
 
 struct GenOp {

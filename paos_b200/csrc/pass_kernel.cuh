@@ -98,6 +98,71 @@ template <typename R> __device__ __noinline__ R readout_value(C<R> v, int what) 
     return v.x * v.x + v.y * v.y;
 }
 
+// ---- tilted shapes (wfo.py:243-268 with tilt != None; never produced by paos.core.run) ------------------------
+// signed area of (triangle O,p,q) intersected with the unit disc; the sum over the edges of a counter-clockwise
+// polygon is the area of polygon x disc
+static __device__ __noinline__ double edge_disk_area(double px, double py, double qx, double qy) {
+    const double dx = qx - px, dy = qy - py;
+    const double a = dx * dx + dy * dy, b = px * dx + py * dy, c = px * px + py * py - 1.0;
+    const double disc = b * b - a * c;
+    const double full = 0.5 * atan2(px * qy - py * qx, px * qx + py * qy);  // pure sector
+    if (!(disc > 0.0) || !(a > 0.0)) return full;
+    const double sq = sqrt(disc), t1 = (-b - sq) / a, t2 = (-b + sq) / a;
+    if (!(t2 > 0.0 && t1 < 1.0)) return full;
+    const double ta = fmin(fmax(t1, 0.0), 1.0), tb = fmin(fmax(t2, 0.0), 1.0);
+    const double ax = px + ta * dx, ay = py + ta * dy, bx = px + tb * dx, by = py + tb * dy;
+    double area = 0.5 * (ax * by - ay * bx);
+    if (t1 > 0.0) area += 0.5 * atan2(px * ay - py * ax, px * ax + py * ay);
+    if (t2 < 1.0) area += 0.5 * atan2(bx * qy - by * qx, bx * qx + by * qy);
+    return area;
+}
+
+static __device__ __noinline__ double tilted_ellipse_fraction(const GenOp& g, double ix, double iy) {
+    const double ct = g.p7, st = -g.p8;  // rotate by -theta into the ellipse frame
+    const double cx = ix - g.p0, cy = iy - g.p1;
+    const double u0 = (cx * ct - cy * st) * g.p2, v0 = (cx * st + cy * ct) * g.p3;
+    const double r2 = u0 * u0 + v0 * v0;
+    if (r2 <= g.p5) return 1.0;
+    if (r2 >= g.p6) return 0.0;
+    double ux[4], uy[4];
+    const double ox[4] = {-0.5, 0.5, 0.5, -0.5}, oy[4] = {-0.5, -0.5, 0.5, 0.5};
+    for (int k = 0; k < 4; ++k) {
+        const double x = cx + ox[k], y = cy + oy[k];
+        ux[k] = (x * ct - y * st) * g.p2;
+        uy[k] = (x * st + y * ct) * g.p3;
+    }
+    double area = 0.0;
+    for (int k = 0; k < 4; ++k) area += edge_disk_area(ux[k], uy[k], ux[(k + 1) & 3], uy[(k + 1) & 3]);
+    double f = area * g.p4;
+    if (f < 1e-14) f = 0.0;  // a pixel that only grazes the ellipse: the published routine returns exactly 0 / 1
+    if (f > 1.0 - 1e-14) f = 1.0;
+    return f;
+}
+
+static __device__ __noinline__ double tilted_rect_fraction(const GenOp& g, double ix, double iy) {
+    const double ct = g.p7, st = g.p8;
+    const double x0 = (ix - 0.5) - g.p0, y0 = (iy - 0.5) - g.p1;
+    // quick decision from the pixel centre: the pixel spans at most h in either rectangle axis
+    const double xm = x0 + 0.5, ym = y0 + 0.5, h = 0.5 * (fabs(ct) + fabs(st));
+    const double xt0 = fabs(ym * st + xm * ct), yt0 = fabs(ym * ct - xm * st);
+    if (xt0 + h < g.p2 && yt0 + h < g.p3) return 1.0;
+    if (xt0 - h >= g.p2 || yt0 - h >= g.p3) return 0.0;
+    // 32 x 32 sub-pixel centres, accumulated like the published routine (x = x0 - d/2; x += d; same for y)
+    const double d = 1.0 / 32.0;
+    int cnt = 0;
+    double x = x0 - 0.5 * d;
+    for (int i = 0; i < 32; ++i) {
+        x += d;
+        double y = y0 - 0.5 * d;
+        for (int j = 0; j < 32; ++j) {
+            y += d;
+            const double xt = y * st + x * ct, yt = y * ct - x * st;
+            if (fabs(xt) < g.p2 && fabs(yt) < g.p3) ++cnt;
+        }
+    }
+    return (double)cnt / 1024.0;
+}
+
 // Slow path of one general factor at pixel (ix, iy): exact edge-pixel overlap, phase screens, the PSD filter.
 // Out of line on purpose: this is cold code next to the line FFT, and inlining it per register element made
 // the kernel 250 KB of SASS.  Returns the complex factor (fr, fi).
@@ -117,6 +182,13 @@ static __device__ __noinline__ void gen_factor_slow(const GenOp& g, int ix, int 
     }
     fr = re;
     fi = im;
+}
+
+// tilted shapes, kept apart so that the edge-pixel path above stays small
+static __device__ __noinline__ double gen_factor_tilt(const GenOp& g, int ix, int iy) {
+    const double m = g.kind == GEN_ELLIPSE_TILT ? tilted_ellipse_fraction(g, (double)ix, (double)iy)
+                                                : tilted_rect_fraction(g, (double)ix, (double)iy);
+    return g.flag ? 1.0 - m : m;
 }
 
 // single-op version used by the stop reduction (aux_kernels.cu)
@@ -142,6 +214,8 @@ __device__ __forceinline__ void apply_gen(C<R>& v, const GenOp& g, int ix, int i
             re = g.flag ? 1.0 - m : m;
         } break;
         case GEN_SCALE_DEV: re = __ldg((const double*)g.ptr0); break;
+        case GEN_ELLIPSE_TILT:
+        case GEN_RECT_TILT: re = gen_factor_tilt(g, ix, iy); break;
         default: break;
     }
     (void)im;
@@ -260,6 +334,12 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
                     const R m = (R)__ldg((const double*)g.ptr0);
 #pragma unroll
                     for (int j = 0; j < E; ++j) v[j] = v[j] * m;
+                } else if (g.kind == GEN_ELLIPSE_TILT || g.kind == GEN_RECT_TILT) {
+#pragma unroll
+                    for (int j = 0; j < E; ++j) {
+                        const int idx = t + j * T;
+                        v[j] = v[j] * (R)gen_factor_tilt(g, COL ? line : idx, COL ? idx : line);
+                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < E; ++j) {

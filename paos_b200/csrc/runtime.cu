@@ -738,10 +738,33 @@ static void push_gen(paos_wfo* w, const GenOp& g) {
 
 int paos_wfo_aperture(paos_wfo* w, int shape, double ixc, double iyc, double ihx, double ihy, double theta, int obscuration) {
     if (!w) return fail(PAOS_ERR_ARG, "null handle");
-    if (theta != 0.0) return fail(PAOS_ERR_UNSUPPORTED, "tilted apertures are not implemented (paos/core/run.py:114-121 never tilts)");
     if (!(ihx > 0.0) || !(ihy > 0.0) || !std::isfinite(ixc) || !std::isfinite(iyc)) return fail(PAOS_ERR_ARG, "bad aperture geometry");
     GenOp g{};
     g.flag = obscuration ? 1 : 0;
+    if (theta != 0.0 && (shape == PAOS_SHAPE_ELLIPSE || shape == PAOS_SHAPE_RECT)) {
+        // tilted shapes (never produced by paos.core.run): general factors evaluated per pixel, quick interior / exterior
+        // decision first, exact overlap (ellipse) or 32x32 sub-pixel count (rectangle) at the edge
+        if (!std::isfinite(theta)) return fail(PAOS_ERR_ARG, "bad aperture tilt");
+        g.p0 = ixc;
+        g.p1 = iyc;
+        g.p7 = std::cos(theta);
+        g.p8 = std::sin(theta);
+        if (shape == PAOS_SHAPE_ELLIPSE) {
+            g.kind = GEN_ELLIPSE_TILT;
+            g.p2 = 1.0 / ihx;
+            g.p3 = 1.0 / ihy;
+            g.p4 = ihx * ihy;
+            const double d = std::sqrt(0.5) * std::max(g.p2, g.p3) * (1.0 + 1e-9) + 1e-12;  // pixel half-diagonal, worst axis
+            g.p5 = d < 1.0 ? (1.0 - d) * (1.0 - d) : -1.0;
+            g.p6 = (1.0 + d) * (1.0 + d);
+        } else {
+            g.kind = GEN_RECT_TILT;
+            g.p2 = ihx / 2.0;
+            g.p3 = ihy / 2.0;
+        }
+        push_gen(w, g);
+        return PAOS_OK;
+    }
     if (shape == PAOS_SHAPE_ELLIPSE) {
         g.kind = GEN_ELLIPSE;
         g.p0 = ixc;

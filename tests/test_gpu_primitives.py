@@ -260,3 +260,17 @@ def test_grid_sag_needing_resampling_is_refused():
     w = paos_b200.WFO(1.0, 1e-6, 128, 2)
     with pytest.raises(NotImplementedError):
         w.grid_sag(np.ones((128, 128)) * 1e-9, 128, 128, 0.7 * w.dx, 0.7 * w.dy)
+
+
+@pytest.mark.parametrize("tilt", [17.0, -63.0, 90.0])
+def test_tilted_apertures(tilt):
+    """tilt != None (wfo.py:243-268); paos.core.run never tilts, so these take the per-pixel path."""
+    n = 64
+    p = Pair(1.0, 1e-6, n, 1)
+    p.call("aperture", 0.03, -0.02, hx=0.31, hy=0.17, shape="elliptical", tilt=tilt)
+    p.check(1e-13)
+    p.call("aperture", -0.05, 0.04, hx=0.22, hy=0.07, shape="rectangular", tilt=tilt, obscuration=True)
+    p.check(1e-13)
+    p.call("make_stop")
+    p.call("ptp", 50.0)
+    p.check()
