@@ -72,6 +72,8 @@ int paos_wfo_create(paos_wfo **out, int n, int dtype, int device, void *stream, 
 int paos_wfo_destroy(paos_wfo *w);
 /* reset to the initial all-ones field (re-use of a handle for the next chain) */
 int paos_wfo_reset(paos_wfo *w);
+/* same thing under the name the reference's constructor suggests (wfo.py:118: np.ones) */
+int paos_wfo_fill_ones(paos_wfo *w);
 /* run everything recorded so far (asynchronous) */
 int paos_wfo_flush(paos_wfo *w);
 /* flush and wait for the stream */

@@ -48,6 +48,7 @@ SIGNATURES = {
     "paos_wfo_create": (_i, [C.POINTER(_vp), _i, _i, _i, _vp, _vp]),
     "paos_wfo_destroy": (_i, [_vp]),
     "paos_wfo_reset": (_i, [_vp]),
+    "paos_wfo_fill_ones": (_i, [_vp]),
     "paos_wfo_flush": (_i, [_vp]),
     "paos_wfo_sync": (_i, [_vp]),
     "paos_wfo_upload": (_i, [_vp, _vp]),

@@ -648,6 +648,8 @@ int paos_wfo_reset(paos_wfo* w) {
     return PAOS_OK;
 }
 
+int paos_wfo_fill_ones(paos_wfo* w) { return paos_wfo_reset(w); }
+
 int paos_wfo_flush(paos_wfo* w) {
     if (!w) return fail(PAOS_ERR_ARG, "null handle");
     return flush_all(w);
