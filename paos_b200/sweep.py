@@ -73,12 +73,16 @@ def bind_to_gpu_numa(device):
 class Sweep:
     """Persistent executor for jobs of one grid size on one GPU."""
 
-    def __init__(self, gridsize, device=0, dtype="complex128", slots=3, what="psf"):
+    def __init__(self, gridsize, device=0, dtype="complex128", slots=None, what="psf"):
         import torch
 
         if what not in READS:
             raise ValueError(f"what must be one of {sorted(READS)}")
         self.n = int(gridsize)
+        if slots is None:
+            # 2048^2 and up: a pass fills the machine, 3 slots only overlap the tails; smaller grids are launch-bound and
+            # gain from more host threads / streams (measured: 512^2 AIRS 9.8 k -> 13.9 k PSF/s from 3 to 6 slots)
+            slots = 3 if self.n >= 2048 else 6
         self.device = int(device)
         self.dtype = dtype
         self.what = what

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--cpu", action="store_true", help="also time one job of each config on the numpy oracle")
     ap.add_argument("--only", default="")
     ap.add_argument("--dtype", default="complex128")
+    ap.add_argument("--slots", type=int, default=None)
     args = ap.parse_args()
     import torch
 
@@ -43,7 +44,7 @@ def main():
             continue
         jobs, mode = make()
         n = jobs[0]["gridsize"]
-        sw = Sweep(n, slots=3, what="psf", dtype=args.dtype)
+        sw = Sweep(n, slots=args.slots, what="psf", dtype=args.dtype)
         stack = sw.empty_stack(len(jobs))
         sw.run(jobs, out=stack)  # warm-up (also compiles the native surface records of every job: parse-time work)
         st0 = sw.stats()
