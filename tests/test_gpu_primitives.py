@@ -274,3 +274,38 @@ def test_tilted_apertures(tilt):
     p.call("make_stop")
     p.call("ptp", 50.0)
     p.check()
+
+
+def test_planner_limits_and_degenerate_masks():
+    """More general factors than one pass holds (GMAX = 12), more chained FFTs than one pass holds (16), an aperture
+    that misses the grid (every line blanked) and one smaller than a pixel."""
+    n = 128
+    p = Pair(1.0, 2e-6, n, 2, field=random_field(n, 8))
+    for k in range(15):  # 15 masks in a row, no FFT between them: more than GMAX in one position
+        p.call("aperture", 0.01 * (k - 7), 0.0, hx=0.9 - 0.01 * k, hy=0.8, shape="elliptical")
+    p.check()
+    for k in range(10):  # 20 FFT2 with only separable factors between them: two passes per axis
+        p.call("ptp", 20.0 + k)
+    p.check()
+    p.call("aperture", 0.0, 0.0, hx=0.003, hy=0.002, shape="elliptical")  # smaller than a pixel (dx = 1/64)
+    p.call("ptp", 5.0)
+    p.check()
+    p.call("aperture", 5.0, 5.0, hx=0.1, hy=0.1, shape="elliptical")  # misses the grid: everything is blanked
+    p.call("ptp", 5.0)
+    assert np.count_nonzero(p.d.wfo) == 0 and np.count_nonzero(p.o._wfo) == 0
+    assert np.count_nonzero(p.d.psf) == 0
+
+
+def test_two_stops_and_obscured_stop():
+    n = 128
+    p = Pair(1.0, 2e-6, n, 2, field=random_field(n, 9))
+    p.call("aperture", 0.0, 0.0, r=0.45, shape="circular")
+    p.call("aperture", 0.0, 0.0, r=0.1, shape="circular", obscuration=True)
+    p.call("make_stop")
+    p.call("ptp", 30.0)
+    p.call("aperture", 0.02, 0.0, hx=0.5, hy=0.2, shape="rectangular")
+    p.call("make_stop")
+    p.call("lens", 3.0)
+    p.call("propagate", 3.0)
+    e = p.check()
+    assert abs(np.sum(p.o.amplitude**2) - 1.0) < 1e-12, e
