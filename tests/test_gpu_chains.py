@@ -203,3 +203,27 @@ def test_hand_built_chain_with_orthonormal_zernikes():
     got, ref = both(job)
     assert sorted(ref) == [2, 3, 4, 5] and ref[3]["wfe"] is not None
     compare(got, ref, TOL["complex128"])
+
+
+def test_sweep_host_ring_and_python_fallback():
+    """A pinned host stack shorter than the job list is used as a ring; jobs the native runner refuses (orthonormal
+    Zernikes) fall back to the Python driver inside the same sweep."""
+    import paos_b200
+    from paos_b200 import configs
+    from paos_b200.sweep import Sweep
+
+    jobs = configs.fgs1_montecarlo(grid=256, realizations=[0, 1, 2, 3, 4])
+    z1 = [it for it in jobs[2]["opt_chain"].values() if it["type"] == "Zernike"][0]
+    z1["Zorthonorm"] = True
+    z1["aperture"] = dict(shape="elliptical", type="aperture", xrad=0.009, yrad=0.008, xc=np.nan, yc=np.nan)
+    sw = Sweep(256, slots=2, what="amplitude")
+    ring = sw.empty_stack(2, host=True)
+    out, meta = sw.run(jobs, host_out=ring)
+    out = out.cpu().numpy()
+    assert len(meta) == 5 and all(m is not None for m in meta)
+    # slot k % 2 of the ring holds the last job written to it: jobs 4 and 3
+    assert np.array_equal(ring[0].numpy(), out[4]) and np.array_equal(ring[1].numpy(), out[3])
+    for k in (1, 2):
+        job = jobs[k]
+        ref = paos_b200.run(job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"], job["opt_chain"])
+        assert relerr(out[k], ref[max(ref)]["amplitude"]) <= 1e-12
