@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PAOS_ABI_VERSION 1
+#define PAOS_ABI_VERSION 2
 #define PAOS_MAX_CHAINED_FFTS 16 /* line FFTs one pass kernel can chain */
 
 enum {
@@ -177,6 +177,8 @@ typedef struct paos_surface {
     double cout_t;                              /* item["ABCDt"].cout (+1 / -1)                         */
     double xdec, ydec, xrot, yrot;              /* Coordinate Break (NaN = 0)                            */
     double zernike_radius;                      /* NaN = use wz (run.py:131)                             */
+    double screen_dx, screen_dy;                /* pixel pitch `screen` was resampled to (wfo.py:848-862); the chain stops
+                                                   with PAOS_ERR_UNSUPPORTED if the beam's pitch differs at the surface */
     double psd[8];                              /* A, B, C, fknee, fmin, fmax, SR, unit_scale            */
     uint64_t psd_seed;
     const int *zernike_m, *zernike_n;           /* host arrays [zernike_terms]                           */

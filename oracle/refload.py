@@ -8,7 +8,8 @@ absent from this image:
 * ``astropy.units``        -> tiny unit objects (only ``u.m``, ``u.Unit(str)`` and ``.to()`` are used:
                               ``paos/classes/wfo.py:882``, ``paos/classes/psd.py:148``, ``paos/core/parseConfig.py:275``)
 * ``photutils.aperture``   -> ``oracle.apertures`` (restated masks; parity unpinned, see that module)
-* ``skimage.transform``    -> functions that raise (only reached when a sag map is not on the WFO grid)
+* ``skimage.transform``    -> ``oracle/skimage_np.py`` (restated, parity unpinned; every call is logged in ``SKIMAGE_CALLS``
+  so that a test can assert that the bit-pinned grid-sag cases never reached it)
 * ``matplotlib``/``pyplot``, ``paos.core.plot`` -> empty stubs
 
 Used by ``tests/golden/make_golden.py`` (fixture generation) and by the ``not gpu`` tests that pin
@@ -20,6 +21,7 @@ import sys
 import types
 
 REFERENCE_ROOT = "/root/reference"
+SKIMAGE_CALLS = []  # names of the restated skimage.transform functions the reference has called so far
 
 
 def reference_available():
@@ -90,13 +92,19 @@ def install_stubs():
     sys.modules.setdefault("photutils", phot)
     sys.modules.setdefault("photutils.aperture", phot_ap)
 
-    def _no_skimage(*a, **k):
-        raise RuntimeError("skimage.transform is not available: put the sag map on the WFO grid")
+    from oracle import skimage_np
+
+    def _counted(fn):
+        def wrapper(*a, **k):
+            SKIMAGE_CALLS.append(fn.__name__)
+            return fn(*a, **k)
+
+        return wrapper
 
     sk = types.ModuleType("skimage")
     skt = types.ModuleType("skimage.transform")
-    skt.rescale = _no_skimage
-    skt.resize = _no_skimage
+    skt.rescale = _counted(skimage_np.rescale)
+    skt.resize = _counted(skimage_np.resize)
     sk.transform = skt
     sys.modules.setdefault("skimage", sk)
     sys.modules.setdefault("skimage.transform", skt)

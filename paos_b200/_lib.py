@@ -15,7 +15,7 @@ PAOS_ERR_ARG, PAOS_ERR_CUDA, PAOS_ERR_STATE, PAOS_ERR_UNSUPPORTED = -1, -2, -3, 
 PAOS_C128, PAOS_C64 = 0, 1
 READ_WFO, READ_AMPLITUDE, READ_PHASE, READ_PSF = 0, 1, 2, 3
 SHAPE_ELLIPSE, SHAPE_RECT = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_CHAINED_FFTS = 16
 
 

@@ -24,7 +24,7 @@ class Surface(C.Structure):
         ("ap_xrad", C.c_double), ("ap_yrad", C.c_double), ("ap_xc", C.c_double), ("ap_yc", C.c_double),
         ("abcd_t", C.c_double * 4), ("abcd_s", C.c_double * 4), ("cout_t", C.c_double),
         ("xdec", C.c_double), ("ydec", C.c_double), ("xrot", C.c_double), ("yrot", C.c_double),
-        ("zernike_radius", C.c_double), ("psd", C.c_double * 8), ("psd_seed", C.c_uint64),
+        ("zernike_radius", C.c_double), ("screen_dx", C.c_double), ("screen_dy", C.c_double), ("psd", C.c_double * 8), ("psd_seed", C.c_uint64),
         ("zernike_m", C.POINTER(C.c_int)), ("zernike_n", C.POINTER(C.c_int)), ("zernike_coef", C.POINTER(C.c_double)),
         ("screen", C.POINTER(C.c_double)), ("psd_noise1", C.POINTER(C.c_double)), ("psd_noise2", C.POINTER(C.c_double)),
         ("read_dst", C.c_void_p),
@@ -56,11 +56,17 @@ class CompiledChain:
         self.keep = []
         self.nums = []
         self.saved = []
+        init_pitch = True  # no surface so far can have changed the pixel pitch (no propagation, no magnification)
         for i, item in enumerate(items):
             s = self.array[i]
             kind = item["type"]
             if kind not in _TYPES:
                 raise ValueError(f"Surface Type not recognised: {kind}")
+            if kind == "Grid Sag" and not init_pitch:
+                # wfo.py:848-862 resamples the map to the pitch *at the surface*, which only the scalar walk knows
+                raise NotImplementedError("Grid Sag behind a propagation or magnification: use the Python driver")
+            if item["ABCDt"].thickness != 0 or item["ABCDt"].M != 1 or item["ABCDs"].M != 1:
+                init_pitch = False
             s.type = _TYPES[kind]
             s.is_stop = 1 if item["is_stop"] else 0
             s.save = 1 if item["save"] else 0
@@ -103,6 +109,7 @@ class CompiledChain:
                 s.zernike_radius = float(item["Zradius"])
             elif s.type == SURF_SCREEN:
                 screen = _on_grid_sag(item, self.n, pupil_diameter, zoom)
+                s.screen_dx = s.screen_dy = pupil_diameter * zoom / self.n
                 if device is None:
                     self.keep.append(screen)
                     s.screen = screen.ctypes.data_as(C.POINTER(C.c_double))

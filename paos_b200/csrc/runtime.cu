@@ -436,7 +436,8 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
             for (int p2 = 0; p2 <= pp.P.nfft; ++p2) ntab += pp.P.tab[p2] != nullptr;
             fprintf(stderr, "[plan] %s nfft=%d tables=%d gens=%d (", pp.col ? "col" : "row", pp.P.nfft, ntab, pp.P.ngen);
             for (int g2 = 0; g2 < pp.P.ngen; ++g2) fprintf(stderr, "%d@%d ", pp.P.gen[g2].kind, pp.P.gen[g2].pos);
-            fprintf(stderr, ") ctab=%d%d src=%d\n", pp.P.ctab_in != nullptr, pp.P.ctab_out != nullptr, pp.P.src != nullptr);
+            fprintf(stderr, ") ctab=%d%d src=%d tiles=[%d,%d]\n", pp.P.ctab_in != nullptr, pp.P.ctab_out != nullptr, pp.P.src != nullptr,
+                    pp.P.tile_lo, pp.P.tile_hi == 0x7fffffff ? -1 : pp.P.tile_hi);
         }
     }
     if (readout && !plan.passes.empty()) {
@@ -1376,6 +1377,10 @@ extern "C" int paos_chain_run(paos_wfo* w, double pupil_diameter, double wavelen
                                   s.zernike_origin, b.wl, nullptr);
             if (rc) return rc;
         } else if (s.type == PAOS_SURF_SCREEN) {
+            // the map was resampled on the host for one pixel pitch (wfo.py:848-862 uses the pitch at the surface)
+            if (std::fabs(b.dx - s.screen_dx) > 1e-12 * std::fabs(b.dx) || std::fabs(b.dy - s.screen_dy) > 1e-12 * std::fabs(b.dy))
+                return fail(PAOS_ERR_UNSUPPORTED, "grid-sag screen of surface %d was prepared for pitch (%g, %g) but the beam is sampled at (%g, %g)",
+                            i, s.screen_dx, s.screen_dy, b.dx, b.dy);
             rc = s.screen_on_device ? paos_wfo_phase_screen_device(w, s.screen, b.wl) : paos_wfo_phase_screen(w, s.screen, b.wl);
             if (rc) return rc;
         } else if (s.type == PAOS_SURF_PSD) {

@@ -2,11 +2,20 @@
 padding / cropping to the WFO grid extent, as in steps 1-2 of ``paos/classes/wfo.py:753-845``.  What reaches the device
 is an ``N x N`` float64 screen (0 where masked) that ``paos_wfo_phase_screen`` applies in the fused passes.
 
-Steps 3-4 of the reference (cubic-spline ``rescale`` / ``resize`` with anti-aliasing, ``wfo.py:848-862``) live in
-scikit-image, which is not available here; maps that need them raise ``NotImplementedError`` -- supply the sag at the
-WFO pixel pitch (any extent, any decentre).
+Steps 3-4 of the reference (cubic-spline ``rescale`` / ``resize`` with anti-aliasing, ``wfo.py:848-862``) and the
+up-sampling by 2 for an odd pad / crop difference (``:806-814``) use ``paos_b200/resample.py``, the host-side
+restatement of the scikit-image 0.24 routines the reference calls (parity unpinned: scikit-image is not available here).
 """
 import numpy as np
+
+from .resample import rescale, resize
+
+MAX_MAP_ELEMENTS = 1 << 28  # 2 GiB of float64 per intermediate map: beyond this the pitch is wrong for this grid
+
+
+def _rescale_map(sag, mask, scale_x, scale_y):
+    anti_aliasing = scale_x < 1.0 or scale_y < 1.0  # wfo.py:698-700: only when down-sampling
+    return (rescale(sag, (scale_y, scale_x), anti_aliasing), rescale(mask, (scale_y, scale_x), anti_aliasing))
 
 
 def prepare_sag(sag, nx, ny, delx, dely, xdec, ydec, n, dx, dy):
@@ -27,8 +36,16 @@ def prepare_sag(sag, nx, ny, delx, dely, xdec, ydec, n, dx, dy):
     # step 2: pad or crop to the extent of the WFO grid
     width_diff = int(np.floor((sag.shape[1] * delx - n * dx) / delx))
     height_diff = int(np.floor((sag.shape[0] * dely - n * dy) / dely))
-    if width_diff % 2 == 1 or height_diff % 2 == 1:
-        raise NotImplementedError("odd pad/crop difference: the reference up-samples the map by 2 with skimage.rescale")
+    if max(sag.shape[1] - 2 * min(width_diff, 0), 1) * max(sag.shape[0] - 2 * min(height_diff, 0), 1) > MAX_MAP_ELEMENTS:
+        raise ValueError(f"grid_sag: padding the {sag.shape} map (pitch {delx:g} x {dely:g} m) to the WFO extent "
+                         f"({n * dx:g} x {n * dy:g} m) needs more than {MAX_MAP_ELEMENTS} samples")
+    scale_x = scale_y = 1
+    if width_diff % 2 == 1:  # odd difference: sample twice as finely so that the pad / crop is symmetric (wfo.py:802-814)
+        scale_x, delx, width_diff = 2, delx / 2, width_diff * 2
+    if height_diff % 2 == 1:
+        scale_y, dely, height_diff = 2, dely / 2, height_diff * 2
+    if (scale_x != 1) or (scale_y != 1):
+        sag, mask = _rescale_map(sag, mask, scale_x, scale_y)
 
     def fit(a, diff, axis, fill):
         if diff < 0:
@@ -45,9 +62,13 @@ def prepare_sag(sag, nx, ny, delx, dely, xdec, ydec, n, dx, dy):
     sag, mask = fit(sag, width_diff, 1, 0), fit(mask, width_diff, 1, 1)
     sag, mask = fit(sag, height_diff, 0, 0), fit(mask, height_diff, 0, 1)
 
-    if delx / dx != 1 or dely / dy != 1 or sag.shape != (n, n):
-        raise NotImplementedError(
-            "grid_sag needs the map at the WFO pixel pitch: the reference's cubic rescale/resize (skimage) is not implemented")
+    # step 3: bring the map to the WFO pixel pitch; step 4: force the exact grid shape (can be one pixel off)
+    scale_x, scale_y = delx / dx, dely / dy
+    if (scale_x != 1) or (scale_y != 1):
+        sag, mask = _rescale_map(sag, mask, scale_x, scale_y)
+    if sag.shape != (n, n):
+        anti_aliasing = n / sag.shape[1] < 1.0 or n / sag.shape[0] < 1.0
+        sag, mask = resize(sag, (n, n), anti_aliasing), resize(mask, (n, n), anti_aliasing)
     mask = mask > 0.1
     screen = np.ascontiguousarray(np.where(mask, 0.0, sag), dtype=np.float64)
     return screen, mask

@@ -140,8 +140,13 @@ class Sweep:
                 for idx in cc.saved:
                     cc.set_readout(idx, -1, None)
                 cc.set_readout(cc.saved[-1], code, dst.data_ptr())
-                last = chain_mod.run_compiled(wfo, job, cc)[-1]
-            else:
+                try:
+                    last = chain_mod.run_compiled(wfo, job, cc)[-1]
+                except NotImplementedError:
+                    # the chain met a surface the native runner cannot take as compiled (a grid-sag map behind a change of
+                    # sampling: its screen was resampled for the INIT pitch); the Python driver restarts the job from INIT
+                    use_native = False
+            if not use_native:
                 def snapshot(w, item):
                     _lib.check(_lib.lib.paos_wfo_read_device(w._handle, code, C.c_void_p(dst.data_ptr())))
                     return dict(wz=w.wz, distancetofocus=w.distancetofocus, fratio=w.fratio, dx=w.dx, dy=w.dy, wl=w.wl,

@@ -227,3 +227,48 @@ def test_sweep_host_ring_and_python_fallback():
         job = jobs[k]
         ref = paos_b200.run(job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"], job["opt_chain"])
         assert relerr(out[k], ref[max(ref)]["amplitude"]) <= 1e-12
+
+
+def test_grid_sag_chain_off_pitch_map(tmp_path):
+    """Config 5 with the map supplied at twice the WFO pitch and an odd size: the chain goes through the resampling
+    branches of grid_sag (wfo.py:802-862)."""
+    from paos_b200 import configs
+
+    job = configs.grid_sag(grid=256, wavelengths=(3.0,), light_output=False, workdir=str(tmp_path))[0]
+    item = [it for it in job["opt_chain"].values() if it["type"] == "Grid Sag"][0]
+    coarse = np.array(item["grid_sag"][::2, ::2][:127, :])
+    item.update(grid_sag=coarse, nx=coarse.shape[1], ny=coarse.shape[0], delx=2 * item["delx"], dely=2 * item["dely"])
+    got, ref = both(job)
+    compare(got, ref, TOL["complex128"])
+
+
+def test_sweep_grid_sag_behind_a_change_of_sampling(tmp_path):
+    """A Grid Sag surface after a propagation that changed the pixel pitch: the native chain runner refuses its INIT-pitch
+    screen (PAOS_ERR_UNSUPPORTED) and Sweep reruns the job through the Python driver, which resamples at the surface."""
+    import copy
+
+    from oracle import paos_np
+    from paos_b200 import configs
+    from paos_b200.sweep import Sweep
+
+    n = 256
+    job = configs.grid_sag(grid=n, wavelengths=(3.0,), light_output=True, workdir=str(tmp_path))[0]
+    chain = job["opt_chain"]
+    args = lambda c: (job["pupil_diameter"], job["wavelength"], n, job["zoom"], job["field"], c)
+    probe = copy.deepcopy(chain)
+    for it in probe.values():
+        it["save"] = True
+    dx5 = paos_np.run(*args(probe))[5]["dx"]  # pitch at surface 5, after the 55 m propagation
+    assert dx5 != job["pupil_diameter"] * job["zoom"] / n
+    second = copy.deepcopy(chain[3])
+    yy, xx = np.mgrid[0:90, 0:70]
+    second.update(num=5.5, name="Sag2", grid_sag=20e-9 * np.cos(xx / 9.0) * np.sin(yy / 7.0) + 1e-9, nx=70, ny=90,
+                  delx=1.7 * dx5, dely=1.7 * dx5, xdec=0.0, ydec=0.0, save=False)
+    items = sorted(list(chain.items()) + [(5.5, second)], key=lambda kv: kv[0])
+    job["opt_chain"] = dict(items)
+    sw = Sweep(n, slots=1, what="amplitude")
+    out, meta = sw.run([job])
+    ref = paos_np.run(*args(job["opt_chain"]))
+    last = ref[max(ref)]
+    assert relerr(out[0].cpu().numpy(), last["amplitude"]) <= TOL["complex128"]
+    assert meta[0]["dx"] == last["dx"]

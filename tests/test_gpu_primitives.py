@@ -254,12 +254,25 @@ def test_grid_sag_pad_crop_decentre(ny, nx, xdec, ydec):
     p.check()
 
 
-def test_grid_sag_needing_resampling_is_refused():
-    import paos_b200
-
-    w = paos_b200.WFO(1.0, 1e-6, 128, 2)
-    with pytest.raises(NotImplementedError):
-        w.grid_sag(np.ones((128, 128)) * 1e-9, 128, 128, 0.7 * w.dx, 0.7 * w.dy)
+@pytest.mark.parametrize("ny,nx,pitch,xdec,ydec", [
+    (128, 128, (0.7, 0.7), 0.0, 0.0), (80, 96, (1.9, 1.6), 0.0, 0.0), (129, 128, (1.0, 1.0), 0.0, 0.0),
+    (101, 155, (1.3, 0.8), -0.7, 2.2),
+])
+def test_grid_sag_resampled(ny, nx, pitch, xdec, ydec):
+    """Maps that are not at the WFO pixel pitch (wfo.py:696-751, :802-814, :848-862): host resampler + fused phase multiply
+    against the oracle's restated skimage flow."""
+    n = 128
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[0:ny, 0:nx]
+    sag = 30e-9 * np.cos(2 * np.pi * xx / 17.0) * np.sin(2 * np.pi * yy / 13.0) + rng.standard_normal((ny, nx)) * 1e-9
+    sag[:4, :] = 0.0
+    sag[7, 9] = np.nan
+    p = Pair(1.0, 1e-6, n, 2)
+    d = p.d.dx
+    ro, rd = p.call("grid_sag", sag, nx, ny, pitch[0] * d, pitch[1] * d, xdec, ydec)
+    assert np.array_equal(ro.mask, rd.mask)
+    assert relerr(rd.filled(0), ro.filled(0)) <= 1e-12
+    p.check()
 
 
 @pytest.mark.parametrize("tilt", [17.0, -63.0, 90.0])

@@ -124,3 +124,48 @@ def test_gather_stack_world_size_2_gloo(tmp_path):
     port = 29600 + os.getpid() % 300
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok")
+
+
+@pytest.mark.parametrize("ny,nx,pitch,xdec,ydec", [
+    (64, 64, (0.7, 0.7), 0.0, 0.0), (40, 48, (1.9, 1.6), 0.0, 0.0), (65, 64, (1.0, 1.0), 0.0, 0.0),
+    (51, 77, (1.3, 0.8), -0.7, 2.2), (838 // 4, 1158 // 4, (0.37, 0.37), 0.0, 0.0),
+])
+def test_grid_sag_resampling_matches_oracle(ny, nx, pitch, xdec, ydec):
+    """paos_b200.sag.prepare_sag (own separable cubic resampler) against the oracle's grid_sag (scipy.ndimage restatement
+    of the skimage calls, wfo.py:696-862): same mask, same screen to rounding."""
+    from oracle import paos_np
+    from paos_b200.sag import prepare_sag
+
+    n = 64
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:ny, 0:nx]
+    sag = 30e-9 * np.cos(2 * np.pi * xx / 17.0) * np.sin(2 * np.pi * yy / 13.0) + rng.standard_normal((ny, nx)) * 1e-9
+    sag[:3, :] = 0.0
+    sag[5, 7] = np.nan
+    o = paos_np.WFO(1.0, 1e-6, n, 2)
+    ro = o.grid_sag(sag.copy(), nx, ny, pitch[0] * o.dx, pitch[1] * o.dy, xdec, ydec)
+    screen, mask = prepare_sag(sag.copy(), nx, ny, pitch[0] * o.dx, pitch[1] * o.dy, xdec, ydec, n, o.dx, o.dy)
+    assert screen.shape == (n, n) and np.array_equal(mask, ro.mask)
+    assert np.max(np.abs(screen - ro.filled(0))) <= 1e-12 * np.max(np.abs(ro.filled(0)))
+
+
+def test_resampler_known_answers():
+    """Properties of the cubic resampler that hold whatever library restates it: constants and linear ramps inside the
+    clip range are reproduced, identity scale returns the input, shapes follow round(scale * shape)."""
+    from paos_b200 import resample
+
+    a = np.full((9, 14), 2.5)
+    assert np.allclose(resample.rescale(a, (1.7, 0.6), True), 2.5, atol=1e-14)
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal((12, 10))
+    assert np.max(np.abs(resample.rescale(b, (1.0, 1.0), False) - b)) <= 1e-14
+    assert resample.rescale(b, (2.0, 0.5), True).shape == (24, 5)
+    assert resample.rescale(b, (0.01, 0.01), True).shape == (1, 1)
+    ramp = np.add.outer(np.arange(60.0), 2.0 * np.arange(50.0))
+    up = resample.rescale(ramp, (2.0, 2.0), False)
+    yy = (np.arange(120) + 0.5) / 2 - 0.5
+    xx = (np.arange(100) + 0.5) / 2 - 0.5
+    want = np.add.outer(yy, 2.0 * xx)
+    # a cubic spline reproduces a ramp exactly; the kink of the mirrored border decays as 0.268^k (k input pixels)
+    inner = (slice(36, -36), slice(36, -36))
+    assert np.max(np.abs(up[inner] - want[inner])) <= 1e-7

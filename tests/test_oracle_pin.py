@@ -123,9 +123,10 @@ def test_parse_config_equals_reference(name, data_dir):
 @needs_reference
 @pytest.mark.parametrize("ny,nx,xdec,ydec", [(64, 64, 0.0, 0.0), (48, 40, 0.0, 0.0), (80, 96, 0.0, 0.0), (56, 72, 1.3, -2.6)])
 def test_grid_sag_pad_crop_decentre_equals_reference(ny, nx, xdec, ydec):
-    """Masking, Fourier recentring and pad / crop of a grid-sag map (wfo.py:753-845) against the unmodified reference
-    (its skimage calls are stubbed to raise, so reaching them would fail the test)."""
+    """Masking, Fourier recentring and pad / crop of a grid-sag map (wfo.py:753-845) against the unmodified reference;
+    these cases are bit-pinned because they never reach the (restated) skimage routines."""
     ref = refload.load()
+    calls_before = len(refload.SKIMAGE_CALLS)
     rng = np.random.default_rng(0)
     sag = rng.standard_normal((ny, nx)) * 30e-9
     sag[:3, :] = 0.0
@@ -133,4 +134,35 @@ def test_grid_sag_pad_crop_decentre_equals_reference(ny, nx, xdec, ydec):
     a, b = ref.WFO(1.0, 1e-6, 64, 2), paos_np.WFO(1.0, 1e-6, 64, 2)
     ra = a.grid_sag(sag.copy(), nx, ny, a.dx, a.dy, xdec, ydec)
     rb = b.grid_sag(sag.copy(), nx, ny, b.dx, b.dy, xdec, ydec)
+    assert np.array_equal(a._wfo, b._wfo) and np.array_equal(ra.filled(0), rb.filled(0)) and np.array_equal(ra.mask, rb.mask)
+    assert len(refload.SKIMAGE_CALLS) == calls_before
+
+
+@needs_reference
+@pytest.mark.parametrize("ny,nx,pitch,xdec,ydec,calls", [
+    (64, 64, (0.7, 0.7), 0.0, 0.0, ["rescale"] * 2),                    # finer map: cropped, down-sampled (anti-aliased)
+    (40, 48, (1.9, 1.6), 0.0, 0.0, ["rescale"] * 2 + ["resize"] * 2),   # coarser map: padded, up-sampled, one pixel off -> resized
+    (65, 64, (1.0, 1.0), 0.0, 0.0, ["rescale"] * 4),                    # odd crop difference: up-sampled by 2, cropped, back by 1/2
+    (51, 77, (1.3, 0.8), -0.7, 2.2, ["rescale"] * 4 + ["resize"] * 2),  # all of it, with a decentre
+])
+def test_grid_sag_resampling_control_flow_equals_reference(ny, nx, pitch, xdec, ydec, calls):
+    """The resampling branches of grid_sag (wfo.py:696-751, :802-814, :848-862): the unmodified reference, with its
+    skimage calls routed to oracle/skimage_np.py, against the oracle's restated flow.  This pins every decision around
+    the skimage calls (which branch, which scale, which anti_aliasing flag, which output shape) bit for bit; the
+    interpolation itself stays "parity unpinned" (scikit-image is absent)."""
+    ref = refload.load()
+    rng = np.random.default_rng(3)
+    yy, xx = np.mgrid[0:ny, 0:nx]
+    sag = 30e-9 * np.cos(2 * np.pi * xx / 17.0) * np.sin(2 * np.pi * yy / 13.0) + rng.standard_normal((ny, nx)) * 1e-9
+    sag[:3, :] = 0.0
+    sag[5, 7] = np.nan
+    a, b = ref.WFO(1.0, 1e-6, 64, 2), paos_np.WFO(1.0, 1e-6, 64, 2)
+    before = len(refload.SKIMAGE_CALLS)
+    ra = a.grid_sag(sag.copy(), nx, ny, pitch[0] * a.dx, pitch[1] * a.dy, xdec, ydec)
+    seen = refload.SKIMAGE_CALLS[before:]
+    rb = b.grid_sag(sag.copy(), nx, ny, pitch[0] * b.dx, pitch[1] * b.dy, xdec, ydec)
+    assert seen, "case did not reach the resampling branch"
+    if calls is not None:
+        assert seen == calls
+    assert ra.shape == (64, 64)
     assert np.array_equal(a._wfo, b._wfo) and np.array_equal(ra.filled(0), rb.filled(0)) and np.array_equal(ra.mask, rb.mask)
