@@ -78,6 +78,10 @@ int paos_wfo_fill_ones(paos_wfo *w);
 int paos_wfo_flush(paos_wfo *w);
 /* flush and wait for the stream */
 int paos_wfo_sync(paos_wfo *w);
+/* Flush, then write out the zeros that blanked passes left unwritten ("virtual zeros": lines an aperture blanks are
+ * neither loaded nor stored, the planner only remembers the band outside which the field is zero), so that a
+ * *borrowed* field buffer holds the complete complex array (wfo.py:163-164).  paos_wfo_read* do this themselves. */
+int paos_wfo_materialize(paos_wfo *w);
 
 /* ---- data movement --------------------------------------------------------------------------- */
 /* replace the field by host data (n*n complex, dtype of the handle); discards recorded operations */

@@ -168,6 +168,27 @@ cudaError_t launch_norm2(const void* src, int n, int dtype, const GenOp* gen, in
     return cudaGetLastError();
 }
 
+// ---- virtual zeros made real -----------------------------------------------------------------------------
+// A blanked pass leaves the lines outside a band untouched (pass_kernel.cuh); before anything other than a pass kernel
+// reads the field (a copy of the complex array, the stand-alone read-out, a stop reduction on a stored field) the
+// zeros are written once.  axis 0: the band is a range of rows, axis 1: a range of columns.
+template <typename R>
+__global__ void __launch_bounds__(256) zero_outside_band_kernel(C<R>* __restrict__ f, int n, int axis, int lo, int hi) {
+    const int y = blockIdx.y;
+    if (axis == 0 && y >= lo && y <= hi) return;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) {
+        if (axis == 1 && x >= lo && x <= hi) continue;
+        stc(f + (size_t)y * n + x, C<R>((R)0, (R)0));
+    }
+}
+
+cudaError_t launch_zero_outside_band(void* field, int n, int dtype, int axis, int lo, int hi, cudaStream_t st) {
+    const dim3 grid((n + 255) / 256 < 4 ? (n + 255) / 256 : 4, n);
+    if (dtype == 0) zero_outside_band_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<C<double>*>(field), n, axis, lo, hi);
+    else zero_outside_band_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<C<float>*>(field), n, axis, lo, hi);
+    return cudaGetLastError();
+}
+
 // ---- read-out (wfo.py:163-172, plot.py:125-130) ------------------------------------------------------
 template <typename R>
 __global__ void __launch_bounds__(256) readout_kernel(const C<R>* __restrict__ src, size_t total, int what, R* __restrict__ out) {

@@ -6,6 +6,7 @@ namespace paosb {
 cudaError_t launch_build_tables(const TableBlock& B, cudaStream_t st);
 cudaError_t launch_norm2(const void* src, int n, int dtype, const GenOp* gen, int ngen, double* partials,
                          int npartials, double* out_slot, cudaStream_t st);
+cudaError_t launch_zero_outside_band(void* field, int n, int dtype, int axis, int lo, int hi, cudaStream_t st);
 cudaError_t launch_readout(const void* src, int n, int dtype, int what, void* out, cudaStream_t st);
 cudaError_t launch_zernike(const ZernParams& Z, const unsigned char* mask, double* out, cudaStream_t st);
 cudaError_t launch_zernike_cov(const ZernParams& Z, const unsigned char* mask, double* partial, int blocks, cudaStream_t st);

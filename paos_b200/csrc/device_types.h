@@ -44,8 +44,12 @@ struct PassParams {
     const void* ctab_out;      // same, applied after the last position
     unsigned genmask;          // bit p set: some general factor sits at position p
     unsigned sgnmask;          // bit p set: position p carries the sign (-1)^index (no table)
-    int tile_lo, tile_hi;      // tiles outside this range are blanked by an aperture of this pass: store zeros only
+    int tile_lo, tile_hi;      // tiles outside this range end the pass exactly zero (aperture bounding box, or zero on input):
+                               // they are not touched at all -- the planner remembers the band (virtual zeros)
+    int in_lo, in_hi;          // along-line index range outside which the input is (virtually) zero: not loaded
     int readout;               // 0: store the complex field; PAOS_READ_* (1..3): store a real read-out into dst_real instead
+    int zero_fill;             // 1: blank tiles store zeros into the field (diagnostic mode PAOS_ZERO_FILL=1)
+    int tile_base;             // set by the launcher: tile of CTA 0 (blank tiles are not launched unless they have to store)
     int pad;
     void* dst_real;
     GenOp gen[GMAX];

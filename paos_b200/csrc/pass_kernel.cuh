@@ -231,14 +231,14 @@ __device__ __noinline__ void store_zero_tile(const PassParams& P) {
     const int tid = threadIdx.x;
     const int w = COL ? (tid % W) : (tid / T);
     const int t = COL ? (tid / W) : (tid % T);
-    const int line = blockIdx.x * W + w;
+    const int line = ((int)blockIdx.x + P.tile_base) * W + w;
     C<R>* dst = reinterpret_cast<C<R>*>(P.dst);
     R* out = reinterpret_cast<R*>(P.dst_real);
     const C<R> zero((R)0, (R)0);
     for (int j = 0; j < E; ++j) {
         const int idx = t + j * T;
         const size_t ga = COL ? ((size_t)idx * N + line) : ((size_t)line * N + idx);
-        stc_stream(dst + ga, zero);
+        if (P.zero_fill) stc_stream(dst + ga, zero);
         if (P.readout) out[ga] = (R)0;  // |0|, angle(0), |0|^2
     }
 }
@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
     const int tid = threadIdx.x;
     const int w = COL ? (tid % W) : (tid / T);
     const int t = COL ? (tid / W) : (tid % T);
-    const int line = blockIdx.x * W + w;
+    const int tile = (int)blockIdx.x + P.tile_base;
+    const int line = tile * W + w;
     C<R>* sm = smem + w * G::line_stride(COL ? W : 1, (int)sizeof(C<R>));
     auto sync = [] { __syncthreads(); };
 
@@ -262,20 +263,24 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
     C<R>* dst = reinterpret_cast<C<R>*>(P.dst);
 
     // Tiles outside [tile_lo, tile_hi] are blanked by an elliptical aperture somewhere in this pass (the planner
-    // works the range out from the apertures' bounding boxes): such a tile is zero at the end of the pass whatever
-    // happens before the mask, so it is neither loaded nor transformed, only stored as zeros.
-    if ((int)blockIdx.x < P.tile_lo || (int)blockIdx.x > P.tile_hi) {
-        store_zero_tile<R, N, E, W, COL>(P);
+    // works the range out from the apertures' bounding boxes) or are zero on input: such a tile is zero at the end of
+    // the pass whatever happens before the mask, so it is neither loaded, transformed nor stored -- the planner
+    // remembers the band outside which the field is zero ("virtual zeros") and hands it to the next consumer as
+    // [in_lo, in_hi] (other axis) or folds it into its tile range (same axis).  Only a fused read-out needs the zeros.
+    if (tile < P.tile_lo || tile > P.tile_hi) {
+        if (P.zero_fill | P.readout) store_zero_tile<R, N, E, W, COL>(P);
         return;
     }
 
     C<R> v[E];
     if (src) {
+        // memory outside [in_lo, in_hi] is stale: those elements are zeros that were never written
+        const unsigned span = (unsigned)(P.in_hi - P.in_lo);
 #pragma unroll
         for (int j = 0; j < E; ++j) {
             const int idx = t + j * T;
             const size_t ga = COL ? ((size_t)idx * N + line) : ((size_t)line * N + idx);
-            v[j] = ldc_stream(src + ga);
+            v[j] = ((unsigned)(idx - P.in_lo) <= span) ? ldc_stream(src + ga) : C<R>((R)0, (R)0);
         }
     } else {
 #pragma unroll
@@ -425,7 +430,7 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
 
 // host-side launcher table -------------------------------------------------------------------------
 template <typename R, int N, int E, int W, bool COL, int MINB>
-cudaError_t launch_pass_t(const PassParams& P, const void* tw1, const void* tw2, cudaStream_t st, int device) {
+cudaError_t launch_pass_t(const PassParams& P0, const void* tw1, const void* tw2, cudaStream_t st, int device) {
     using G = LineGeom<N, E>;
     constexpr int threads = W * G::T;
     const size_t smem = (size_t)W * G::line_stride(COL ? W : 1, (int)sizeof(C<R>)) * sizeof(C<R>);
@@ -436,7 +441,16 @@ cudaError_t launch_pass_t(const PassParams& P, const void* tw1, const void* tw2,
         if (e != cudaSuccess) return e;
         configured[device & 63] = true;
     }
-    kern<<<N / W, threads, smem, st>>>(P, reinterpret_cast<const C<R>*>(tw1), reinterpret_cast<const C<R>*>(tw2));
+    // blank tiles have nothing to do unless they must store zeros (fused read-out, diagnostic zero fill): launch the rest
+    PassParams P = P0;
+    int tiles = N / W;
+    P.tile_base = 0;
+    if (!P.zero_fill && !P.readout) {
+        P.tile_base = P.tile_lo > 0 ? P.tile_lo : 0;
+        tiles = (P.tile_hi < N / W - 1 ? P.tile_hi : N / W - 1) - P.tile_base + 1;
+        if (tiles <= 0) return cudaSuccess;  // the whole field is (virtually) zero after this pass
+    }
+    kern<<<tiles, threads, smem, st>>>(P, reinterpret_cast<const C<R>*>(tw1), reinterpret_cast<const C<R>*>(tw2));
     return cudaGetLastError();
 }
 

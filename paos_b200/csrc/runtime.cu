@@ -150,6 +150,16 @@ struct PosAcc {  // what accumulates at one position of a pass
     bool trivial() const { return nterms == 0; }  // a real scale and/or the (-1)^k sign: no table needed
 };
 
+// Virtual zeros.  A pass whose tiles outside [tile_lo, tile_hi] end up exactly zero does not store those zeros: the
+// memory of those lines is stale and the planner remembers that the field is zero outside a band of rows (axis 0, left
+// by a row pass) or of columns (axis 1).  The next pass folds the band into its tile range (same axis) or skips the
+// loads outside it (other axis); any other reader of the field has the zeros written first (materialize_band).
+struct ZeroBand {
+    bool valid = false;
+    int axis = 0;
+    int lo = 0, hi = -1;  // lines [lo, hi] may be non-zero (lo > hi: the whole field is zero)
+};
+
 struct TimedLaunch {
     cudaEvent_t a, b;
     int nfft;
@@ -163,6 +173,7 @@ struct paos_wfo {
     void* field = nullptr;
     bool own_field = false;
     bool materialized = false;  // false: the field is all ones and lives nowhere yet
+    ZeroBand band;              // virtual zeros of `field` (see ZeroBand)
     size_t elem = 16;           // bytes per complex element
     Twiddles tw;
     std::vector<Op> ops;
@@ -309,7 +320,39 @@ static int spec_from_acc(paos_wfo* w, const PosAcc& a, Plan& plan, const void** 
 }
 
 // Build the passes for the queued ops.  readout/dst_real: fused read-out for the final pass (0 = none).
-static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int readout, void* dst_real, void* field) {
+// band: virtual zeros of `field` on entry, updated to the state after the last planned pass.
+static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int readout, void* dst_real, void* field, ZeroBand& band) {
+    static const bool zero_fill = getenv("PAOS_ZERO_FILL") != nullptr;  // diagnostic: store the zeros, keep no band
+    // fold the band into a pass on `axis` whose own apertures leave lines [line_lo, line_hi], and advance the band
+    auto finish_pass = [&](PassParams& P, int axis, int line_lo, int line_hi) {
+        const int n = w->n;
+        P.in_lo = 0;
+        P.in_hi = n - 1;
+        if (band.valid && P.src) {
+            if (band.axis == axis) {  // lines outside the band are zero on input, hence on output
+                line_lo = std::max(line_lo, band.lo);
+                line_hi = std::min(line_hi, band.hi);
+            } else {  // every line crosses the band: only that stretch is loaded
+                P.in_lo = band.hi >= band.lo ? band.lo : n;  // empty band: [n, n] matches no index (the kernel tests
+                P.in_hi = band.hi >= band.lo ? band.hi : n;  // (unsigned)(idx - in_lo) <= (unsigned)(in_hi - in_lo))
+            }
+        }
+        P.tile_lo = 0;
+        P.tile_hi = 0x7fffffff;
+        P.zero_fill = zero_fill ? 1 : 0;
+        band.valid = false;
+        if (line_lo > 0 || line_hi < n - 1) {
+            const int W = tile_width(n, w->dtype, axis == 1);
+            P.tile_lo = line_lo / W;
+            P.tile_hi = line_hi >= line_lo ? line_hi / W : -1;  // empty range: everything is blank
+            if (!zero_fill) {
+                band.valid = true;
+                band.axis = axis;
+                band.lo = P.tile_lo * W;
+                band.hi = P.tile_hi < 0 ? -1 : std::min(n - 1, P.tile_hi * W + W - 1);
+            }
+        }
+    };
     std::vector<Item> th[2];
     std::vector<GenOp> gens;
     split_ops(w, ops, th[0], th[1], gens);
@@ -392,13 +435,7 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
             line_lo = std::max(line_lo, (int)std::ceil(c0 - reach));
             line_hi = std::min(line_hi, (int)std::floor(c0 + reach));
         }
-        P.tile_lo = 0;
-        P.tile_hi = 0x7fffffff;
-        if (line_lo > 0 || line_hi < w->n - 1) {
-            const int W = tile_width(w->n, w->dtype, axis == 1);
-            P.tile_lo = line_lo / W;
-            P.tile_hi = line_hi >= line_lo ? line_hi / W : -1;  // empty range: everything is blank
-        }
+        finish_pass(P, axis, line_lo, line_hi);
         for (int p = 0; p <= P.nfft; ++p) {
             P.scl[p] = 1.0;
             P.tab[p] = nullptr;
@@ -423,7 +460,7 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
         P.src = w->materialized ? field : nullptr;
         P.dst = field;
         P.scl[0] = 1.0;
-        P.tile_hi = 0x7fffffff;
+        finish_pass(P, 0, 0, w->n - 1);
         PlannedPass pp;
         pp.col = false;
         pp.P = P;
@@ -436,8 +473,8 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
             for (int p2 = 0; p2 <= pp.P.nfft; ++p2) ntab += pp.P.tab[p2] != nullptr;
             fprintf(stderr, "[plan] %s nfft=%d tables=%d gens=%d (", pp.col ? "col" : "row", pp.P.nfft, ntab, pp.P.ngen);
             for (int g2 = 0; g2 < pp.P.ngen; ++g2) fprintf(stderr, "%d@%d ", pp.P.gen[g2].kind, pp.P.gen[g2].pos);
-            fprintf(stderr, ") ctab=%d%d src=%d tiles=[%d,%d]\n", pp.P.ctab_in != nullptr, pp.P.ctab_out != nullptr, pp.P.src != nullptr,
-                    pp.P.tile_lo, pp.P.tile_hi == 0x7fffffff ? -1 : pp.P.tile_hi);
+            fprintf(stderr, ") ctab=%d%d src=%d tiles=[%d,%d] in=[%d,%d]\n", pp.P.ctab_in != nullptr, pp.P.ctab_out != nullptr,
+                    pp.P.src != nullptr, pp.P.tile_lo, pp.P.tile_hi == 0x7fffffff ? -1 : pp.P.tile_hi, pp.P.in_lo, pp.P.in_hi);
         }
     }
     if (readout && !plan.passes.empty()) {
@@ -519,12 +556,24 @@ static int flush_ops(paos_wfo* w, std::vector<Op>& ops, int readout, void* dst_r
     Plan plan;
     // rectangle count tables are TableSpecs too: they were registered when the op was recorded and live in
     // screens (see paos_wfo_aperture)
-    rc = build_plan(w, ops, plan, readout, dst_real, w->field);
+    ZeroBand band = w->band;
+    rc = build_plan(w, ops, plan, readout, dst_real, w->field, band);
     if (rc) return rc;
     rc = run_plan(w, plan);
     if (rc) return rc;
     ops.clear();
     w->materialized = true;
+    w->band = band;
+    return PAOS_OK;
+}
+
+// write the virtual zeros of `field` (see ZeroBand) before something other than a pass kernel reads it
+static int materialize_band(paos_wfo* w, void* field, ZeroBand& band) {
+    if (!band.valid) return PAOS_OK;
+    cudaError_t e = launch_zero_outside_band(field, w->n, w->dtype, band.axis, band.lo, band.hi, w->stream);
+    if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "zero fill launch failed: %s", cudaGetErrorString(e));
+    w->stats.kernel_launches++;
+    band.valid = false;
     return PAOS_OK;
 }
 
@@ -646,6 +695,7 @@ int paos_wfo_reset(paos_wfo* w) {
     w->ops.clear();
     recycle_screens(w);
     w->materialized = false;
+    w->band.valid = false;
     return PAOS_OK;
 }
 
@@ -654,6 +704,13 @@ int paos_wfo_fill_ones(paos_wfo* w) { return paos_wfo_reset(w); }
 int paos_wfo_flush(paos_wfo* w) {
     if (!w) return fail(PAOS_ERR_ARG, "null handle");
     return flush_all(w);
+}
+
+int paos_wfo_materialize(paos_wfo* w) {
+    if (!w) return fail(PAOS_ERR_ARG, "null handle");
+    int rc = flush_all(w);
+    if (rc) return rc;
+    return materialize_band(w, w->field, w->band);
 }
 
 int paos_wfo_sync(paos_wfo* w) {
@@ -673,6 +730,7 @@ int paos_wfo_upload(paos_wfo* w, const void* host_src) {
     CU(cudaMemcpyAsync(w->field, host_src, (size_t)w->n * w->n * w->elem, cudaMemcpyHostToDevice, w->stream));
     CU(cudaStreamSynchronize(w->stream));
     w->materialized = true;
+    w->band.valid = false;
     return PAOS_OK;
 }
 
@@ -685,6 +743,7 @@ int paos_wfo_upload_device(paos_wfo* w, const void* dev_src) {
     if (dev_src != w->field)
         CU(cudaMemcpyAsync(w->field, dev_src, (size_t)w->n * w->n * w->elem, cudaMemcpyDeviceToDevice, w->stream));
     w->materialized = true;
+    w->band.valid = false;
     return PAOS_OK;
 }
 
@@ -696,6 +755,8 @@ static int read_impl(paos_wfo* w, int what, void* dst, bool to_host) {
     const size_t nn = (size_t)w->n * w->n;
     if (what == PAOS_READ_WFO) {
         rc = flush_all(w);
+        if (rc) return rc;
+        rc = materialize_band(w, w->field, w->band);
         if (rc) return rc;
         CU(cudaMemcpyAsync(dst, w->field, nn * w->elem, to_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, w->stream));
     } else {
@@ -711,6 +772,8 @@ static int read_impl(paos_wfo* w, int what, void* dst, bool to_host) {
             rc = flush_all(w, what, dev_out);  // read-out fused into the last pass
             if (rc) return rc;
         } else {
+            rc = materialize_band(w, w->field, w->band);
+            if (rc) return rc;
             cudaError_t e = launch_readout(w->field, w->n, w->dtype, what, dev_out, w->stream);
             if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "read-out launch failed: %s", cudaGetErrorString(e));
             w->stats.kernel_launches++;
@@ -852,6 +915,7 @@ int paos_wfo_make_stop(paos_wfo* w) {
         if (rc) return rc;
     }
     w->ops = tail;
+    if (w->materialized && (rc = materialize_band(w, w->field, w->band))) return rc;
     double* slot = w->slots + 2 * (w->slot_next++ % paos_wfo::NSLOTS);
     cudaError_t e = launch_norm2(w->materialized ? w->field : nullptr, w->n, w->dtype, gens.data(), (int)gens.size(), w->partials,
                                  paos_wfo::NPARTIALS, slot, w->stream);
@@ -1015,10 +1079,13 @@ static int run_on_scratch(paos_wfo* w, std::vector<Op>& ops) {
     Plan plan;
     const bool mat = w->materialized;
     w->materialized = true;  // the scratch field has data
-    rc = build_plan(w, ops, plan, 0, nullptr, w->scratch_field);
+    ZeroBand band;  // the scratch field arrives fully written
+    rc = build_plan(w, ops, plan, 0, nullptr, w->scratch_field, band);
     w->materialized = mat;
     if (rc) return rc;
-    return run_plan(w, plan);
+    rc = run_plan(w, plan);
+    if (rc) return rc;
+    return materialize_band(w, w->scratch_field, band);  // its readers are plain kernels
 }
 
 int paos_wfo_psd(paos_wfo* w, double A, double B, double C, double fknee, double fmin, double fmax, double SR,

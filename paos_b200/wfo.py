@@ -187,6 +187,12 @@ class WFO:
     def flush(self):
         check(lib.paos_wfo_flush(self._handle))
 
+    def field_tensor(self):
+        """The torch CUDA tensor that owns the wavefront (no copy; valid once the WFO's stream has caught up).  Lines that
+        an aperture blanked are normally never written (``paos_wfo_materialize``), so they are written out first."""
+        check(lib.paos_wfo_materialize(self._handle))
+        return self._buf
+
     def sync(self):
         check(lib.paos_wfo_sync(self._handle))
 

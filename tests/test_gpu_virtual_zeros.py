@@ -1,0 +1,96 @@
+"""GPU tests of the "virtual zeros" bookkeeping: lines blanked by an aperture are neither loaded nor stored, the planner
+remembers the zero band and every other reader of the field sees real zeros."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import Pair, TOL, random_field, relerr
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("n", [128, 512])
+def test_every_reader_sees_the_zeros(n):
+    """aperture -> flush leaves stale memory outside the aperture's rows; the complex copy, the stand-alone read-outs and
+    the borrowed tensor must all show zeros there, also when the stale content was random data."""
+    p = Pair(1.0, 1e-6, n, 4, field=random_field(n, 3))
+    p.call("aperture", 0.03, -0.02, hx=0.21, hy=0.13, shape="elliptical")
+    p.d.flush()
+    st = p.d.stats()
+    amp = p.d.amplitude          # stand-alone read-out kernel on a field with a band
+    assert relerr(amp, p.o.amplitude) <= 1e-12
+    assert relerr(p.d.wfo, p.o._wfo) <= 1e-12
+    t = p.d.field_tensor()
+    p.d.sync()
+    assert relerr(t.cpu().numpy(), p.o._wfo) <= 1e-12
+    assert p.d.stats()["kernel_launches"] > st["kernel_launches"]
+    p.check()
+
+
+def test_band_handed_from_pass_to_pass():
+    """rows blanked -> column pass loads only the band -> columns blanked -> row pass; reads in between and at the end."""
+    n = 256
+    p = Pair(1.0, 2e-6, n, 4, field=random_field(n, 5))
+    p.call("aperture", 0.0, 0.05, hx=0.3, hy=0.1, shape="elliptical")
+    p.call("lens", 3.0)
+    p.call("propagate", 1.5)
+    p.check()
+    d = p.o.dx
+    p.call("aperture", -3 * d, 0.0, hx=20 * d, hy=60 * d, shape="elliptical")
+    p.call("propagate", 0.7)
+    d = p.o.dx
+    p.call("aperture", 0.0, 0.0, hx=80 * d, hy=50 * d, shape="rectangular")
+    p.call("make_stop")
+    p.call("propagate", 0.8)
+    p.check()
+
+
+def test_stop_reduction_on_a_banded_field():
+    n = 256
+    p = Pair(1.0, 2e-6, n, 4, field=random_field(n, 7))
+    p.call("aperture", 0.0, 0.0, hx=0.2, hy=0.3, shape="elliptical")
+    p.d.flush()               # band left in memory
+    p.call("make_stop")       # reduction reads the stored field
+    p.check()
+    assert abs(np.sum(np.abs(p.d.wfo) ** 2) - 1.0) <= 1e-12
+
+
+def test_aperture_that_misses_the_grid():
+    """an aperture whose bounding box misses the grid blanks everything (empty band)"""
+    n = 128
+    p = Pair(1.0, 1e-6, n, 1, field=random_field(n, 9))
+    p.call("aperture", 5.0, 0.0, hx=0.1, hy=0.1, shape="elliptical")
+    p.call("lens", 2.0)
+    p.call("propagate", 1.0)
+    assert np.all(p.o._wfo == 0)
+    assert np.all(p.d.wfo == 0) and np.all(p.d.amplitude == 0)
+
+
+_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+from paos_b200 import configs
+from paos_b200.sweep import Sweep
+jobs = configs.airs_ch0(grid=256, n_wl=3) + configs.hubble(grid=256)
+sw = Sweep(256, slots=1, what="amplitude")
+out, _ = sw.run(jobs)
+np.save({path!r}, out.cpu().numpy())
+"""
+
+
+def test_zero_fill_mode_gives_identical_results(tmp_path):
+    """PAOS_ZERO_FILL=1 (zeros really stored, no band kept) and the default (virtual zeros) must agree bit for bit."""
+    outs = []
+    for mode in ("0", "1"):
+        path = str(tmp_path / f"amp_{mode}.npy")
+        env = dict(os.environ)
+        env.pop("PAOS_ZERO_FILL", None)
+        if mode == "1":
+            env["PAOS_ZERO_FILL"] = "1"
+        subprocess.run([sys.executable, "-c", _SCRIPT.format(root=ROOT, path=path)], check=True, env=env, timeout=300)
+        outs.append(np.load(path))
+    assert outs[0].shape == outs[1].shape and np.array_equal(outs[0], outs[1])
