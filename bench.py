@@ -115,8 +115,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Ariel_AIRS-CH0.ini 2048^2 complex128, wavelengths of the 256-point 1.95-3.9 um sweep, "
-                               "IMAGE_PLANE only", "grid": GRID},
+        "config": {"workload": f"Ariel_AIRS-CH0.ini {GRID}^2 complex128, {N_WL} wavelengths 1.95-3.9 um per GPU "
+                               f"(rank r = field point r), IMAGE_PLANE |.|^2 only",
+                   "grid": GRID, "wavelengths_per_gpu": N_WL,
+                   "sample": f"each step propagates {procs} wavelengths spread evenly over that sweep (one per host core); "
+                             "PSF/s = wavelengths / wall time"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
                          "sample": f"{procs} wavelengths per step (one numpy process each), {args.steps} steps, {warm_done} warm-up steps run"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -136,11 +139,12 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.t_mark = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
             return
@@ -149,7 +153,13 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            if self.t_mark is not None and time.perf_counter() >= self.t_mark:
+                self.lines.append(ln.strip())
+
+    def mark(self):
+        """Start of the timed region: nvidia-smi has been running since start() (it needs a few 100 ms to come up), only
+        samples taken from now on are kept."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -248,13 +258,14 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident throughput ("value") -------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         sw.run(jobs, out=stack)
     barrier()
     st0 = sw.stats()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     t_host0 = time.perf_counter()
     ms = timed_steps(torch, sw, jobs, stack, None, args.steps)
     t_host = time.perf_counter() - t_host0
@@ -383,7 +394,7 @@ def main():
     ap.add_argument("--dtype", default="complex128", choices=["complex128", "complex64"])
     ap.add_argument("--grid", type=int, default=GRID)
     ap.add_argument("--n-wl", type=int, default=N_WL)
-    ap.add_argument("--slots", type=int, default=3)
+    ap.add_argument("--slots", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:

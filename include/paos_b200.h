@@ -60,6 +60,9 @@ typedef struct paos_wfo paos_wfo; /* opaque */
 /* ---- library ------------------------------------------------------------------------------- */
 int paos_abi_version(void);
 const char *paos_last_error(void);
+/* sizeof of a public struct as this library was compiled (0: paos_surface, 1: paos_snapshot, 2: paos_stats; -1 for
+ * anything else): lets a foreign-function binding check its own mirror of the layout */
+long paos_abi_struct_size(int which);
 /* number of usable sm_100 devices (0 when none); never fails */
 int paos_device_count(void);
 
@@ -91,6 +94,10 @@ int paos_wfo_upload(paos_wfo *w, const void *host_src);
 int paos_wfo_read(paos_wfo *w, int what, void *host_dst);
 /* same, into device memory (asynchronous on the handle's stream) */
 int paos_wfo_read_device(paos_wfo *w, int what, void *dev_dst);
+/* Same for |.|, angle or |.|^2 when this read-out is the last use of the wavefront (the IMAGE_PLANE PSF of a sweep,
+ * pipeline.py:112-115 `light_output`): the pass that produces it does not store the complex field.  Afterwards
+ * the handle only accepts paos_wfo_reset / _upload / _destroy (anything else: PAOS_ERR_STATE). */
+int paos_wfo_read_device_final(paos_wfo *w, int what, void *dev_dst);
 /* replace the field by n*n complex elements already in device memory (asynchronous; a no-op copy when
  * dev_src is the handle's own buffer, i.e. the caller wrote into the borrowed tensor) */
 int paos_wfo_upload_device(paos_wfo *w, const void *dev_src);
@@ -176,6 +183,8 @@ typedef struct paos_surface {
     int zernike_terms;
     int zernike_origin;    /* 0 = 'x', 1 = 'y' */
     int screen_on_device;  /* PAOS_SURF_SCREEN: `screen` is a device pointer that stays valid until the chain has run */
+    int read_discard;      /* last surface only: its read-out is final (paos_wfo_read_device_final)                  */
+    int reserved;
     double ap_xrad, ap_yrad, ap_xc, ap_yc;      /* as in opt_chain[..]["aperture"]; NaN centre = follow the chief ray */
     double abcd_t[4], abcd_s[4];                /* row-major A, B, C, D of item["ABCDt"], item["ABCDs"]   */
     double cout_t;                              /* item["ABCDt"].cout (+1 / -1)                         */

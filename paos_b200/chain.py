@@ -20,7 +20,7 @@ class Surface(C.Structure):
     _fields_ = [
         ("type", C.c_int), ("is_stop", C.c_int), ("save", C.c_int), ("has_aperture", C.c_int), ("ap_shape", C.c_int),
         ("ap_obscuration", C.c_int), ("read_what", C.c_int), ("zernike_terms", C.c_int), ("zernike_origin", C.c_int),
-        ("screen_on_device", C.c_int),
+        ("screen_on_device", C.c_int), ("read_discard", C.c_int), ("reserved", C.c_int),
         ("ap_xrad", C.c_double), ("ap_yrad", C.c_double), ("ap_xc", C.c_double), ("ap_yc", C.c_double),
         ("abcd_t", C.c_double * 4), ("abcd_s", C.c_double * 4), ("cout_t", C.c_double),
         ("xdec", C.c_double), ("ydec", C.c_double), ("xrot", C.c_double), ("yrot", C.c_double),
@@ -144,10 +144,12 @@ class CompiledChain:
         self.final = Snapshot()
         self.nsnap = C.c_int(0)
 
-    def set_readout(self, surface_index, what, dev_ptr):
+    def set_readout(self, surface_index, what, dev_ptr, final=False):
+        """``final``: the read-out is the last use of the wavefront (honoured for the last surface of the chain only)."""
         s = self.array[surface_index]
         s.read_what = int(what)
         s.read_dst = dev_ptr
+        s.read_discard = 1 if final else 0
 
 
 def _on_grid_sag(item, n, pupil_diameter, zoom):

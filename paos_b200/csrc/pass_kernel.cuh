@@ -238,7 +238,7 @@ __device__ __noinline__ void store_zero_tile(const PassParams& P) {
     for (int j = 0; j < E; ++j) {
         const int idx = t + j * T;
         const size_t ga = COL ? ((size_t)idx * N + line) : ((size_t)line * N + idx);
-        if (P.zero_fill) stc_stream(dst + ga, zero);
+        if (P.zero_fill && dst) stc_stream(dst + ga, zero);
         if (P.readout) out[ga] = (R)0;  // |0|, angle(0), |0|^2
     }
 }
@@ -408,11 +408,13 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
         for (int j = 0; j < E; ++j) v[j] = v[j] * c;
     }
 
+    if (dst) {  // null: a final read-out, the field itself is not needed any more
 #pragma unroll
-    for (int j = 0; j < E; ++j) {
-        const int idx = t + j * T;
-        const size_t ga = COL ? ((size_t)idx * N + line) : ((size_t)line * N + idx);
-        stc_stream(dst + ga, v[j]);
+        for (int j = 0; j < E; ++j) {
+            const int idx = t + j * T;
+            const size_t ga = COL ? ((size_t)idx * N + line) : ((size_t)line * N + idx);
+            stc_stream(dst + ga, v[j]);
+        }
     }
     if (P.readout) {
         // fused read-out (wfo.py:167-172, plot.py:125-130) so a snapshot costs no extra sweep

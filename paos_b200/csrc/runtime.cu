@@ -174,6 +174,7 @@ struct paos_wfo {
     bool own_field = false;
     bool materialized = false;  // false: the field is all ones and lives nowhere yet
     ZeroBand band;              // virtual zeros of `field` (see ZeroBand)
+    bool dropped = false;       // a final read-out skipped the field store: only reset / upload make the handle usable again
     size_t elem = 16;           // bytes per complex element
     Twiddles tw;
     std::vector<Op> ops;
@@ -545,8 +546,9 @@ static int run_plan(paos_wfo* w, Plan& plan) {
 }
 
 // flush `ops` (a prefix of the queue or all of it)
-static int flush_ops(paos_wfo* w, std::vector<Op>& ops, int readout, void* dst_real) {
+static int flush_ops(paos_wfo* w, std::vector<Op>& ops, int readout, void* dst_real, bool discard = false) {
     if (ops.empty() && w->materialized && !readout) return PAOS_OK;
+    if (w->dropped) return fail(PAOS_ERR_STATE, "the field was discarded by a final read-out: reset the handle before re-using it");
     int rc = set_device(w);
     if (rc) return rc;
     // worst case: every op opens two tables per axis
@@ -559,6 +561,10 @@ static int flush_ops(paos_wfo* w, std::vector<Op>& ops, int readout, void* dst_r
     ZeroBand band = w->band;
     rc = build_plan(w, ops, plan, readout, dst_real, w->field, band);
     if (rc) return rc;
+    if (discard && readout && !plan.passes.empty()) {
+        plan.passes.back().P.dst = nullptr;  // the last pass writes the read-out only
+        w->dropped = true;
+    }
     rc = run_plan(w, plan);
     if (rc) return rc;
     ops.clear();
@@ -577,8 +583,8 @@ static int materialize_band(paos_wfo* w, void* field, ZeroBand& band) {
     return PAOS_OK;
 }
 
-static int flush_all(paos_wfo* w, int readout = 0, void* dst_real = nullptr) {
-    int rc = flush_ops(w, w->ops, readout, dst_real);
+static int flush_all(paos_wfo* w, int readout = 0, void* dst_real = nullptr, bool discard = false) {
+    int rc = flush_ops(w, w->ops, readout, dst_real, discard);
     if (rc) return rc;
     recycle_screens(w);
     return PAOS_OK;
@@ -604,6 +610,14 @@ extern "C" {
 
 int paos_abi_version(void) { return PAOS_ABI_VERSION; }
 const char* paos_last_error(void) { return g_last_error.c_str(); }
+long paos_abi_struct_size(int which) {
+    switch (which) {
+        case 0: return (long)sizeof(paos_surface);
+        case 1: return (long)sizeof(paos_snapshot);
+        case 2: return (long)sizeof(paos_stats);
+        default: return -1;
+    }
+}
 
 int paos_device_count(void) {
     int n = 0;
@@ -696,6 +710,7 @@ int paos_wfo_reset(paos_wfo* w) {
     recycle_screens(w);
     w->materialized = false;
     w->band.valid = false;
+    w->dropped = false;
     return PAOS_OK;
 }
 
@@ -731,6 +746,7 @@ int paos_wfo_upload(paos_wfo* w, const void* host_src) {
     CU(cudaStreamSynchronize(w->stream));
     w->materialized = true;
     w->band.valid = false;
+    w->dropped = false;
     return PAOS_OK;
 }
 
@@ -744,12 +760,14 @@ int paos_wfo_upload_device(paos_wfo* w, const void* dev_src) {
         CU(cudaMemcpyAsync(w->field, dev_src, (size_t)w->n * w->n * w->elem, cudaMemcpyDeviceToDevice, w->stream));
     w->materialized = true;
     w->band.valid = false;
+    w->dropped = false;
     return PAOS_OK;
 }
 
-static int read_impl(paos_wfo* w, int what, void* dst, bool to_host) {
+static int read_impl(paos_wfo* w, int what, void* dst, bool to_host, bool discard = false) {
     if (!w || !dst) return fail(PAOS_ERR_ARG, "null argument");
     if (what < PAOS_READ_WFO || what > PAOS_READ_PSF) return fail(PAOS_ERR_ARG, "unknown read-out %d", what);
+    if (w->dropped) return fail(PAOS_ERR_STATE, "the field was discarded by a final read-out: reset the handle before re-using it");
     int rc = set_device(w);
     if (rc) return rc;
     const size_t nn = (size_t)w->n * w->n;
@@ -769,7 +787,7 @@ static int read_impl(paos_wfo* w, int what, void* dst, bool to_host) {
             dev_out = staging;
         }
         if (!w->ops.empty() || !w->materialized) {
-            rc = flush_all(w, what, dev_out);  // read-out fused into the last pass
+            rc = flush_all(w, what, dev_out, discard && !to_host);  // read-out fused into the last pass
             if (rc) return rc;
         } else {
             rc = materialize_band(w, w->field, w->band);
@@ -793,6 +811,10 @@ static int read_impl(paos_wfo* w, int what, void* dst, bool to_host) {
 
 int paos_wfo_read(paos_wfo* w, int what, void* host_dst) { return read_impl(w, what, host_dst, true); }
 int paos_wfo_read_device(paos_wfo* w, int what, void* dev_dst) { return read_impl(w, what, dev_dst, false); }
+int paos_wfo_read_device_final(paos_wfo* w, int what, void* dev_dst) {
+    if (what == PAOS_READ_WFO) return fail(PAOS_ERR_ARG, "a final read-out is |.|, angle or |.|^2");
+    return read_impl(w, what, dev_dst, false, true);
+}
 
 // ---- elementwise operators -----------------------------------------------------------------------
 static void push_gen(paos_wfo* w, const GenOp& g) {
@@ -1458,7 +1480,12 @@ extern "C" int paos_chain_run(paos_wfo* w, double pupil_diameter, double wavelen
             if (rc) return rc;
         }
         if (s.save) {
-            if (s.read_what >= 0 && s.read_dst && (rc = paos_wfo_read_device(w, s.read_what, s.read_dst))) return rc;
+            if (s.read_what >= 0 && s.read_dst) {
+                // the read-out of the last surface may drop the field: nothing can observe it before the next reset
+                const bool fin = s.read_discard && i == n_surfaces - 1 && s.read_what != PAOS_READ_WFO;
+                rc = fin ? paos_wfo_read_device_final(w, s.read_what, s.read_dst) : paos_wfo_read_device(w, s.read_what, s.read_dst);
+                if (rc) return rc;
+            }
             if (snapshots && nsnap < max_snapshots) fill_snapshot(snapshots[nsnap], i, b, vt, vs);
             ++nsnap;
         }
@@ -1479,6 +1506,7 @@ extern "C" int paos_chain_run(paos_wfo* w, double pupil_diameter, double wavelen
         const double vs0 = As * vs[0] + Bs * vs[1], vs1 = Cs * vs[0] + Ds * vs[1];
         vt[0] = vt0; vt[1] = vt1; vs[0] = vs0; vs[1] = vs1;
     }
+    if (w->dropped) w->ops.clear();  // what the last surface queued behind its final read-out can never be observed
     if (n_snapshots) *n_snapshots = nsnap;
     if (final_state) fill_snapshot(*final_state, n_surfaces, b, vt, vs);
     return PAOS_OK;

@@ -80,9 +80,11 @@ class Sweep:
             raise ValueError(f"what must be one of {sorted(READS)}")
         self.n = int(gridsize)
         if slots is None:
-            # 2048^2 and up: a pass fills the machine, 3 slots only overlap the tails; smaller grids are launch-bound and
-            # gain from more host threads / streams (measured: 512^2 AIRS 9.8 k -> 13.9 k PSF/s from 3 to 6 slots)
-            slots = 3 if self.n >= 2048 else 6
+            # 2048^2 and up: a pass fills the machine, extra slots only overlap the tails and the device-to-host copies
+            # (measured at 2048^2: device-resident throughput equal from 2 to 6 slots, end to end +4 % from 3 to 4);
+            # smaller grids are launch-bound and gain from more host threads / streams (512^2 AIRS 9.8 k -> 13.9 k
+            # PSF/s from 3 to 6 slots)
+            slots = 4 if self.n >= 2048 else 6
         self.device = int(device)
         self.dtype = dtype
         self.what = what
@@ -139,7 +141,8 @@ class Sweep:
                     raise ValueError(f"job {job.get('tag', k)} saves no surface")
                 for idx in cc.saved:
                     cc.set_readout(idx, -1, None)
-                cc.set_readout(cc.saved[-1], code, dst.data_ptr())
+                # the sweep keeps nothing but this read-out: the last pass need not store the complex field
+                cc.set_readout(cc.saved[-1], code, dst.data_ptr(), final=True)
                 try:
                     last = chain_mod.run_compiled(wfo, job, cc)[-1]
                 except NotImplementedError:

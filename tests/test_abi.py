@@ -74,3 +74,13 @@ def test_library_is_built_for_sm100a_only():
         pytest.skip("cuobjdump not available")
     archs = set(re.findall(r"sm_(\d+a?)", out))
     assert archs == {"100a"}, archs
+
+
+def test_ctypes_mirrors_have_the_compiled_layout():
+    """paos_surface / paos_snapshot / paos_stats as mirrored in Python have the size the library was compiled with."""
+    from paos_b200 import _lib, chain
+
+    assert _lib.lib.paos_abi_struct_size(0) == C.sizeof(chain.Surface)
+    assert _lib.lib.paos_abi_struct_size(1) == C.sizeof(chain.Snapshot)
+    assert _lib.lib.paos_abi_struct_size(2) == C.sizeof(_lib.PaosStats)
+    assert _lib.lib.paos_abi_struct_size(99) == -1

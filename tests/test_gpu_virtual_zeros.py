@@ -94,3 +94,54 @@ def test_zero_fill_mode_gives_identical_results(tmp_path):
         subprocess.run([sys.executable, "-c", _SCRIPT.format(root=ROOT, path=path)], check=True, env=env, timeout=300)
         outs.append(np.load(path))
     assert outs[0].shape == outs[1].shape and np.array_equal(outs[0], outs[1])
+
+
+def test_final_read_out_drops_the_field_and_says_so():
+    """paos_wfo_read_device_final: same numbers as the ordinary read-out; afterwards the handle refuses work until it is
+    reset."""
+    import ctypes as C
+
+    import torch
+
+    import paos_b200
+    from paos_b200 import _lib
+
+    n = 256
+    res = []
+    for final in (False, True):
+        w = paos_b200.WFO(1.0, 2e-6, n, 4)
+        w.aperture(0.0, 0.0, hx=0.3, hy=0.2, shape="elliptical")
+        w.make_stop()
+        w.lens(2.0)
+        w.propagate(2.0)
+        out = torch.empty((n, n), dtype=torch.float64, device="cuda")
+        fn = _lib.lib.paos_wfo_read_device_final if final else _lib.lib.paos_wfo_read_device
+        _lib.check(fn(w._handle, _lib.READ_PSF, C.c_void_p(out.data_ptr())))
+        w.sync()
+        res.append(out.cpu().numpy())
+        if final:
+            with pytest.raises(paos_b200.PaosError):
+                w.amplitude
+            w.lens(1.0)
+            with pytest.raises(paos_b200.PaosError):
+                w.flush()
+            _lib.check(_lib.lib.paos_wfo_reset(w._handle))
+            assert np.all(w.amplitude == 1.0)
+    assert np.array_equal(res[0], res[1]) and res[0].sum() > 0.99
+    with pytest.raises(ValueError):
+        w2 = paos_b200.WFO(1.0, 2e-6, n, 4)
+        _lib.check(_lib.lib.paos_wfo_read_device_final(w2._handle, _lib.READ_WFO, C.c_void_p(out.data_ptr())))
+
+
+def test_sweep_slot_is_reusable_after_final_read_outs():
+    from paos_b200 import configs
+    from paos_b200.sweep import Sweep
+
+    jobs = configs.airs_ch0(grid=256, n_wl=4)
+    sw = Sweep(256, slots=1, what="psf")
+    a, _ = sw.run(jobs)
+    a = a.cpu().numpy().copy()
+    b, _ = sw.run(jobs)  # same slots again: every chain starts with a reset
+    assert np.array_equal(a, b.cpu().numpy())
+    energy = a.sum(axis=(1, 2))  # normalised at the stop, then clipped by the apertures behind it
+    assert np.all(energy > 0.1) and np.all(energy <= 1.0 + 1e-9), energy
