@@ -210,6 +210,22 @@ def timed_steps(torch, sweep, jobs, stack, host_stack, steps):
     return start.elapsed_time(end)
 
 
+def fp64_view(grid, dtype, st0, st1, pass_ms, peaks):
+    """The pipe that actually bounds the pass kernel: FP64 instructions of the butterflies of the
+    lines really transformed / pass-kernel time, against 64 FP64 instructions per clock per SM."""
+    lines = int(st1["lines_transformed"] - st0["lines_transformed"])
+    batches = int(st1["line_ffts_run"] - st0["line_ffts_run"])
+    out = {"lines_transformed": lines, "active_line_fraction": lines / max(batches * grid, 1)}
+    if grid == 2048 and dtype == "complex128" and pass_ms:
+        per_line = 532 * 128  # SASS count of one 2048-point line FFT: 320 DADD + 138 DFMA + 74 DMUL per thread, 128 threads
+        clk = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+        peak = 64 * 148 * clk
+        out.update({"instr_per_line_fft": per_line, "achieved_Ginstr_s": lines * per_line / (pass_ms * 1e-3) / 1e9,
+                    "peak_Ginstr_s": peak / 1e9, "frac": lines * per_line / (pass_ms * 1e-3) / peak,
+                    "note": "butterflies only (table and mask multiplies not counted); peak = 64 FP64 instr/clk/SM x 148 SMs x max SM clock"})
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -307,8 +323,10 @@ def run_ours(args):
         sub = jobs[: min(len(jobs), 32)]
         sw1.run(sub, out=stack[: len(sub)])
         sw1.timing_detail(reset=True)
+        s1a = sw1.stats()
         sw1.run(sub, out=stack[: len(sub)])
         det = sw1.timing_detail(reset=True)
+        s1b = sw1.stats()
         sw1.enable_timing(False)
         del sw1
         elem = 16 if args.dtype == "complex128" else 8
@@ -340,6 +358,7 @@ def run_ours(args):
                     "algorithmic_bytes_per_launch": alg / max(tot_launch, 1),
                     "sweep_GBps": actual, "sweep_frac": actual / peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                    "fp64": fp64_view(grid, args.dtype, s1a, s1b, tot_ms, peaks),
                     "note": "achieved counts 32*N^2 B per line-FFT sweep (SURVEY 8d: 64*N^2 per FFT2); a pass chains several "
                             "line FFTs per sweep and lines blanked by an aperture mask are neither loaded nor transformed, so achieved exceeds "
                             "the HBM peak; sweep_GBps = upper bound of the real read+write bytes of the field / time"}

@@ -219,6 +219,7 @@ typedef struct paos_stats {
     uint64_t pass_launches;     /* of which FFT line-pass kernels */
     uint64_t fft2_recorded;     /* FFT2s requested through the API (algorithmic count) */
     uint64_t line_ffts_run;     /* 1-D line-FFT batches executed (2 per FFT2) */
+    uint64_t lines_transformed; /* single lines actually transformed (a batch is n lines unless an aperture blanks some) */
     double last_flush_ms;       /* device time of the most recent flushed batch (CUDA events), 0 if untimed */
 } paos_stats;
 int paos_wfo_stats(paos_wfo *w, paos_stats *out);

@@ -33,6 +33,7 @@ class PaosStats(C.Structure):
         ("pass_launches", C.c_uint64),
         ("fft2_recorded", C.c_uint64),
         ("line_ffts_run", C.c_uint64),
+        ("lines_transformed", C.c_uint64),
         ("last_flush_ms", C.c_double),
     ]
 

@@ -508,6 +508,11 @@ static int launch_pass(paos_wfo* w, bool col, const PassParams& P) {
     w->stats.kernel_launches++;
     w->stats.pass_launches++;
     w->stats.line_ffts_run += (uint64_t)P.nfft;
+    {
+        const int W = tile_width(w->n, w->dtype, col), tiles = w->n / W;
+        const int active = std::max(0, std::min(P.tile_hi, tiles - 1) - std::max(P.tile_lo, 0) + 1);
+        w->stats.lines_transformed += (uint64_t)P.nfft * (uint64_t)active * (uint64_t)W;
+    }
     return PAOS_OK;
 }
 

@@ -81,10 +81,18 @@ def main():
         summary["launch_list"] = launches(args.launches)
     if os.path.exists(args.rep):
         summary["full_capture"] = full(args.rep)
-        reads = [k["dram__bytes_read.sum [Mbyte]"] for k in summary["full_capture"] if "dram__bytes_read.sum [Mbyte]" in k]
-        writes = [k["dram__bytes_write.sum [Mbyte]"] for k in summary["full_capture"] if "dram__bytes_write.sum [Mbyte]" in k]
+        def dram_bytes(rec, which):  # ncu picks a unit per column (byte, Kbyte, Mbyte, Gbyte)
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            for key, val in rec.items():
+                if key.startswith(f"dram__bytes_{which}.sum [") and isinstance(val, float):
+                    return val * scale[key.split("[")[1].rstrip("]")]
+            return None
+
+        reads = [dram_bytes(k, "read") for k in summary["full_capture"]]
+        writes = [dram_bytes(k, "write") for k in summary["full_capture"]]
+        reads, writes = [r for r in reads if r is not None], [w for w in writes if w is not None]
         if reads:
-            per_launch = (sum(reads) + sum(writes)) / len(reads) * 1e6
+            per_launch = (sum(reads) + sum(writes)) / len(reads)
             summary["pass_kernel_bytes_per_launch"] = per_launch
             with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as fh:
                 json.dump({"pass_kernel_bytes_per_launch": per_launch, "from": f"profiles/{args.tag}_ncu_summary.json",
