@@ -213,6 +213,16 @@ int paos_chain_run(paos_wfo *w, double pupil_diameter, double wavelength, double
                    const paos_surface *surfaces, int n_surfaces, paos_snapshot *snapshots, int max_snapshots,
                    int *n_snapshots, paos_snapshot *final_state);
 
+/* ---- encircled energy (docs/source/user/aberration/index.rst:47-67; the reference documents it but has no code) ---
+ * psf_dev: n*n reals on the handle's device (double for a complex128 handle, float for complex64), e.g. the
+ * destination of paos_wfo_read_device(PAOS_READ_PSF).  Pixel (ix, iy) sits at x = (ix - xc)*dx, y = (iy - yc)*dy
+ * (the WFO grid has xc = yc = n/2); r_unit = F# * lambda converts metres to the normalised radius R_f; the curve is
+ * sampled at R_f = (k + 1) * r_max / nbins, k = 0 .. nbins-1.  ee_dev_out receives nbins + 1 doubles on the device:
+ * the fraction of the total energy inside each radius, then the total energy itself.  nbins <= 4096.  Asynchronous
+ * on the handle's stream; the curve is 8*(nbins+1) bytes instead of the 8*n*n of the PSF (what a sweep gathers). */
+int paos_encircled_energy(paos_wfo *w, const void *psf_dev, double dx, double dy, double xc, double yc, double r_unit,
+                          double r_max, int nbins, double *ee_dev_out);
+
 /* ---- statistics -------------------------------------------------------------------------------- */
 typedef struct paos_stats {
     uint64_t kernel_launches;   /* kernels of this library launched on the handle so far */

@@ -427,4 +427,54 @@ cudaError_t launch_normal(uint64_t seed, uint32_t stream_id, int n, double* out,
     return cudaGetLastError();
 }
 
+// ---- encircled energy (docs/source/user/aberration/index.rst:47-67; no code in the reference) ---------------------------
+// f(R) = sum of the PSF over pixels with r <= R, r = sqrt(x^2 + y^2) / (F# * lambda) in image-space-normalised units,
+// x = (ix - xc) * dx.  Radial histogram in shared memory (bins of width dR, one overflow bin), merged with one atomic
+// per bin and CTA; ee_finish turns the histogram into the cumulative, normalised curve.
+template <typename R>
+__global__ void __launch_bounds__(256) ee_hist_kernel(const R* __restrict__ psf, int n, double dx, double dy, double xc, double yc,
+                                                      double inv_bin, int nbins, double* __restrict__ hist) {
+    extern __shared__ double sh[];
+    for (int b = threadIdx.x; b <= nbins; b += blockDim.x) sh[b] = 0.0;
+    __syncthreads();
+    for (int iy = blockIdx.x; iy < n; iy += gridDim.x) {
+        const double y = ((double)iy - yc) * dy;
+        for (int ix = threadIdx.x; ix < n; ix += blockDim.x) {
+            const double x = ((double)ix - xc) * dx;
+            const double q = sqrt(x * x + y * y) * inv_bin;
+            const int b = q < (double)nbins ? (int)q : nbins;
+            const double v = (double)psf[(size_t)iy * n + ix];
+            if (v != 0.0) atomicAdd(&sh[b], v);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b <= nbins; b += blockDim.x)
+        if (sh[b] != 0.0) atomicAdd(&hist[b], sh[b]);
+}
+
+// one thread: ee[k] = (hist[0] + ... + hist[k]) / total, total includes the overflow bin; ee[nbins] receives the total
+__global__ void ee_finish_kernel(double* __restrict__ hist, int nbins, double* __restrict__ ee) {
+    if (threadIdx.x != 0) return;
+    double total = 0.0;
+    for (int b = 0; b <= nbins; ++b) total += hist[b];
+    double acc = 0.0;
+    for (int b = 0; b < nbins; ++b) {
+        acc += hist[b];
+        ee[b] = total != 0.0 ? acc / total : 0.0;
+    }
+    ee[nbins] = total;
+}
+
+cudaError_t launch_encircled_energy(const void* psf, int n, int real_is_float, double dx, double dy, double xc, double yc,
+                                    double inv_bin, int nbins, double* hist, double* ee, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)(nbins + 1) * sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    const int blocks = n < 148 * 4 ? n : 148 * 4;
+    const size_t smem = (size_t)(nbins + 1) * sizeof(double);
+    if (real_is_float) ee_hist_kernel<float><<<blocks, 256, smem, st>>>(reinterpret_cast<const float*>(psf), n, dx, dy, xc, yc, inv_bin, nbins, hist);
+    else ee_hist_kernel<double><<<blocks, 256, smem, st>>>(reinterpret_cast<const double*>(psf), n, dx, dy, xc, yc, inv_bin, nbins, hist);
+    ee_finish_kernel<<<1, 32, 0, st>>>(hist, nbins, ee);
+    return cudaGetLastError();
+}
+
 }  // namespace paosb

@@ -13,5 +13,7 @@ cudaError_t launch_zernike_cov(const ZernParams& Z, const unsigned char* mask, d
 cudaError_t launch_real_to_complex(const double* src, int n, int dtype, void* dst, cudaStream_t st);
 cudaError_t launch_psd_finalize(const void* f, int n, int dtype, const double* noise2, double SR, double unit,
                                 double* out, cudaStream_t st);
+cudaError_t launch_encircled_energy(const void* psf, int n, int real_is_float, double dx, double dy, double xc, double yc,
+                                    double inv_bin, int nbins, double* hist, double* ee, cudaStream_t st);
 cudaError_t launch_normal(uint64_t seed, uint32_t stream_id, int n, double* out, cudaStream_t st);
 }  // namespace paosb

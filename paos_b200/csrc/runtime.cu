@@ -187,6 +187,7 @@ struct paos_wfo {
     void* scratch_field = nullptr;  // complex scratch for the PSD screen
     double* partials = nullptr;
     double* slots = nullptr;  // stop scalars: pairs (1/sqrt(sum), sum)
+    double* ee_hist = nullptr;  // radial histogram of paos_encircled_energy
     int slot_next = 0;
     static constexpr int NSLOTS = 256;
     static constexpr int NPARTIALS = 148 * 8;
@@ -703,6 +704,7 @@ int paos_wfo_destroy(paos_wfo* w) {
     if (w->partials) cudaFree(w->partials);
     if (w->slots) cudaFree(w->slots);
     if (w->own_field && w->field) cudaFree(w->field);
+    if (w->ee_hist) cudaFree(w->ee_hist);
     if (w->own_stream && w->stream) cudaStreamDestroy(w->stream);
     cudaGetLastError();
     delete w;
@@ -1246,6 +1248,22 @@ int paos_wfo_fft2(paos_wfo* w, int inverse) {
 }
 
 // ---- statistics ----------------------------------------------------------------------------------
+int paos_encircled_energy(paos_wfo* w, const void* psf_dev, double dx, double dy, double xc, double yc, double r_unit,
+                          double r_max, int nbins, double* ee_dev_out) {
+    if (!w || !psf_dev || !ee_dev_out) return fail(PAOS_ERR_ARG, "null argument");
+    if (nbins < 1 || nbins > 4096) return fail(PAOS_ERR_ARG, "nbins %d outside [1, 4096]", nbins);
+    if (!(r_unit > 0) || !(r_max > 0) || !(dx > 0) || !(dy > 0)) return fail(PAOS_ERR_ARG, "dx, dy, r_unit and r_max must be positive");
+    int rc = set_device(w);
+    if (rc) return rc;
+    if (!w->ee_hist) CU(cudaMalloc((void**)&w->ee_hist, (4096 + 2) * sizeof(double)));
+    const double inv_bin = (double)nbins / (r_unit * r_max);
+    cudaError_t e = launch_encircled_energy(psf_dev, w->n, w->dtype == PAOS_C128 ? 0 : 1, dx, dy, xc, yc, inv_bin, nbins, w->ee_hist,
+                                            ee_dev_out, w->stream);
+    if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "encircled-energy launch failed: %s", cudaGetErrorString(e));
+    w->stats.kernel_launches += 2;
+    return PAOS_OK;
+}
+
 int paos_wfo_stats(paos_wfo* w, paos_stats* out) {
     if (!w || !out) return fail(PAOS_ERR_ARG, "null argument");
     *out = w->stats;

@@ -102,8 +102,14 @@ class Sweep:
             return torch.empty((count, self.n, self.n), dtype=self.rdtype, pin_memory=True)
         return torch.empty((count, self.n, self.n), dtype=self.rdtype, device=self.tdev)
 
-    def run(self, jobs, out=None, host_out=None, psd_noise=None, native=True, cache_compiled=True, threads=True):
+    def run(self, jobs, out=None, host_out=None, psd_noise=None, native=True, cache_compiled=True, threads=True,
+            ee=None, ee_out=None, ee_host_out=None):
         """Propagate ``jobs``; the last saved surface of job k is read out (``what``) into ``out[k]``.
+
+        ``ee``: ``dict(r_max=..., nbins=...)`` also reduces every PSF (``what="psf"``) to its encircled-energy curve on the
+        device (``paos_b200/ee.py``) into ``ee_out[k]`` (``[len(jobs), nbins + 1]`` float64, allocated when None) and,
+        if given, the pinned ``ee_host_out``; ``out`` may then be a ring of a multiple of ``slots`` wavefronts, so that a
+        sweep moves kilobytes per PSF instead of ``8 N^2`` bytes.  The curves are returned as ``meta[k]["ee"]`` views.
 
         ``out``: device stack (allocated when None).  ``host_out``: optional pinned host stack that also receives
         every result (asynchronous device-to-host copies inside the pipeline; a stack shorter than ``jobs`` is used
@@ -118,6 +124,15 @@ class Sweep:
             out = self.empty_stack(len(jobs))
         code = READS[self.what]
         nslots = len(self.wfos)
+        if out.shape[0] < len(jobs) and (ee is None or out.shape[0] % nslots):
+            raise ValueError("out is shorter than jobs: only an encircled-energy sweep may use it as a ring, of a multiple of `slots` rows")
+        if ee is not None:
+            if self.what != "psf":
+                raise ValueError("encircled energy needs what='psf'")
+            from . import ee as ee_mod
+
+            if ee_out is None:
+                ee_out = torch.empty((len(jobs), int(ee["nbins"]) + 1), dtype=torch.float64, device=self.tdev)
         from . import chain as chain_mod
 
         meta = [None] * len(jobs)
@@ -125,7 +140,7 @@ class Sweep:
         def do_job(k, job):
             s = k % nslots
             wfo, stream = self.wfos[s], self.streams[s]
-            dst = out[k]
+            dst = out[k % out.shape[0]]
             use_native = native
             if use_native:
                 # whole chain planned and enqueued inside the library (paos_chain_run)
@@ -161,6 +176,13 @@ class Sweep:
                 last = {k2: v for k2, v in last.items() if k2 not in ("aperture", "wfe")}
             last["tag"] = job.get("tag", str(k))
             meta[k] = last
+            if ee is not None:
+                ee_mod.encircled_energy(wfo, dst, last["dx"], last["dy"], last["fratio"], last["wl"], ee.get("r_max", 8.0),
+                                        ee["nbins"], out=ee_out[k])
+                last["ee"] = ee_out[k]
+                if ee_host_out is not None:
+                    with torch.cuda.stream(stream):
+                        ee_host_out[k].copy_(ee_out[k], non_blocking=True)
             if host_out is not None:
                 with torch.cuda.stream(stream):
                     host_out[k % host_out.shape[0]].copy_(dst, non_blocking=True)

@@ -187,6 +187,16 @@ class WFO:
     def flush(self):
         check(lib.paos_wfo_flush(self._handle))
 
+    def encircled_energy(self, r_max=8.0, nbins=256, center=None):
+        """``(R_f, EE)``: fraction of the PSF's energy inside the normalised radius ``R_f`` (``r = R_f * fratio * wl``,
+        ``docs/source/user/aberration/index.rst:47-67``), computed on the device from the current wavefront."""
+        from . import ee
+
+        psf = self.psf_device()
+        curve = ee.encircled_energy(self, psf, self._dx, self._dy, self.fratio, self._wl, r_max, nbins, center)
+        self.sync()
+        return ee.radii(r_max, nbins), curve.cpu().numpy()[:-1]
+
     def field_tensor(self):
         """The torch CUDA tensor that owns the wavefront (no copy; valid once the WFO's stream has caught up).  Lines that
         an aperture blanked are normally never written (``paos_wfo_materialize``), so they are written out first."""

@@ -169,3 +169,17 @@ def test_resampler_known_answers():
     # a cubic spline reproduces a ramp exactly; the kink of the mirrored border decays as 0.268^k (k input pixels)
     inner = (slice(36, -36), slice(36, -36))
     assert np.max(np.abs(up[inner] - want[inner])) <= 1e-7
+
+
+def test_oracle_encircled_energy_of_a_gaussian():
+    """The oracle's discrete encircled energy against the closed form for a Gaussian spot: 1 - exp(-R^2 / (2 sigma^2))."""
+    from oracle import paos_np
+
+    n, dx, sigma = 512, 0.01, 0.2
+    x = (np.arange(n) - n / 2) * dx
+    psf = np.exp(-(x[None, :] ** 2 + x[:, None] ** 2) / (2 * sigma**2))
+    ee, total = paos_np.encircled_energy(psf, dx, dx, 1.0, 1.0, 100)
+    R = (np.arange(100) + 1) / 100.0
+    assert total == pytest.approx(2 * np.pi * sigma**2 / dx**2, rel=1e-6)
+    assert np.max(np.abs(ee - (1 - np.exp(-R**2 / (2 * sigma**2))))) < 8e-3  # pixel-centre binning at dx = sigma/20
+    assert np.all(np.diff(ee) >= 0)
