@@ -319,6 +319,39 @@ def run_ours(args):
     d2h = int(len(jobs) * grid * grid * (8 if args.dtype == "complex128" else 4))
     barrier()
 
+    # ---- the same sweep when its product is the encircled-energy curve of every PSF: the PSFs stay on the
+    # device in a ring of `slots` buffers and 2 KB per PSF crosses PCIe instead of 32 MiB --------------------------------
+    e2e_ee = None
+    if args.dtype == "complex128":
+        nb = 256
+        ring = stack[: args.slots]
+        ee_dev = torch.empty((len(jobs), nb + 1), dtype=torch.float64, device=stack.device)
+        ee_host = torch.empty((len(jobs), nb + 1), dtype=torch.float64, pin_memory=True)
+
+        def ee_steps(steps):
+            cur = torch.cuda.current_stream()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record(cur)
+            for s_ in sw.streams:
+                s_.wait_event(a)
+            for _ in range(steps):
+                sw.run(jobs, out=ring, ee=dict(r_max=8.0, nbins=nb), ee_out=ee_dev, ee_host_out=ee_host, cache_compiled=False)
+            for s_ in sw.streams:
+                e_ = torch.cuda.Event()
+                e_.record(s_)
+                cur.wait_event(e_)
+            b.record(cur)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b)
+
+        ee_steps(1)
+        barrier()
+        ms_ee = max_over_ranks(ee_steps(args.steps))
+        e2e_ee = {"value": total_psf / (ms_ee * 1e-3), "unit": "PSF/s (encircled-energy curves to host)",
+                  "d2h_bytes_per_step": int(len(jobs) * (nb + 1) * 8) * world}
+        barrier()
+
     # ---- per-kernel timing for the roofline (separate pass: events around every launch) -------------
     roofline = None
     passes = {}
@@ -402,7 +435,7 @@ def run_ours(args):
             "host_plan_ms_per_psf": 1e3 * t_host / (len(jobs) * args.steps),
             "fft2_per_step": int(st1["fft2_recorded"] - st0["fft2_recorded"]) // args.steps * world,
             "pass_launches_per_psf": (st1["pass_launches"] - st0["pass_launches"]) / (len(jobs) * args.steps),
-            "passes": passes, "gather_ms": gather_ms, "gather_first_ms": gather_first_ms,
+            "e2e_ee": e2e_ee, "passes": passes, "gather_ms": gather_ms, "gather_first_ms": gather_first_ms,
         }
         emit(line)
     if world > 1:

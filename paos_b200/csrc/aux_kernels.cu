@@ -444,7 +444,12 @@ __global__ void __launch_bounds__(256) ee_hist_kernel(const R* __restrict__ psf,
             const double q = sqrt(x * x + y * y) * inv_bin;
             const int b = q < (double)nbins ? (int)q : nbins;
             const double v = (double)psf[(size_t)iy * n + ix];
-            if (v != 0.0) atomicAdd(&sh[b], v);
+            // lanes of a warp that hit the same bin (coarse bins: all 32 of them) add up in registers first; the
+            // shared-memory double atomic is a compare-and-swap loop and serialises on equal addresses
+            const unsigned peers = __match_any_sync(0xffffffffu, b);
+            double tot = 0.0;
+            for (unsigned rem = peers; rem; rem &= rem - 1) tot += __shfl_sync(peers, v, __ffs(rem) - 1);
+            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1 && tot != 0.0) atomicAdd(&sh[b], tot);
         }
     }
     __syncthreads();
@@ -452,28 +457,58 @@ __global__ void __launch_bounds__(256) ee_hist_kernel(const R* __restrict__ psf,
         if (sh[b] != 0.0) atomicAdd(&hist[b], sh[b]);
 }
 
-// one thread: ee[k] = (hist[0] + ... + hist[k]) / total, total includes the overflow bin; ee[nbins] receives the total
-__global__ void ee_finish_kernel(double* __restrict__ hist, int nbins, double* __restrict__ ee) {
-    if (threadIdx.x != 0) return;
-    double total = 0.0;
-    for (int b = 0; b <= nbins; ++b) total += hist[b];
-    double acc = 0.0;
-    for (int b = 0; b < nbins; ++b) {
-        acc += hist[b];
-        ee[b] = total != 0.0 ? acc / total : 0.0;
+// one CTA: ee[k] = (hist[0] + ... + hist[k]) / total, total includes the overflow bin; ee[nbins] receives the total.
+// Block-wide scan (5 consecutive bins per thread, 1024 threads >= 4097 bins): a serial loop over global memory cost
+// more than the whole propagation.
+__global__ void __launch_bounds__(1024) ee_finish_kernel(double* __restrict__ hist, int nbins, double* __restrict__ ee) {
+    constexpr int PER = 5;
+    __shared__ double warp_sum[32];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    double v[PER], mine = 0.0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int b = t * PER + k;
+        v[k] = b <= nbins ? hist[b] : 0.0;
+        if (b <= nbins) hist[b] = 0.0;  // leave the histogram clean for the next call on this handle (stream order)
+        mine += v[k];
     }
-    ee[nbins] = total;
+    double incl = mine;  // inclusive scan over the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    if (lane == 31) warp_sum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        double w = warp_sum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += up;
+        }
+        warp_sum[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const double total = warp_sum[31];
+    double acc = (wid ? warp_sum[wid - 1] : 0.0) + (incl - mine);
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int b = t * PER + k;
+        acc += v[k];
+        if (b < nbins) ee[b] = total != 0.0 ? acc / total : 0.0;
+    }
+    if (t == 0) ee[nbins] = total;
 }
 
 cudaError_t launch_encircled_energy(const void* psf, int n, int real_is_float, double dx, double dy, double xc, double yc,
                                     double inv_bin, int nbins, double* hist, double* ee, cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)(nbins + 1) * sizeof(double), st);
-    if (e != cudaSuccess) return e;
+    // `hist` is all zeros on entry: zeroed at allocation and by ee_finish_kernel after every use
     const int blocks = n < 148 * 4 ? n : 148 * 4;
     const size_t smem = (size_t)(nbins + 1) * sizeof(double);
     if (real_is_float) ee_hist_kernel<float><<<blocks, 256, smem, st>>>(reinterpret_cast<const float*>(psf), n, dx, dy, xc, yc, inv_bin, nbins, hist);
     else ee_hist_kernel<double><<<blocks, 256, smem, st>>>(reinterpret_cast<const double*>(psf), n, dx, dy, xc, yc, inv_bin, nbins, hist);
-    ee_finish_kernel<<<1, 32, 0, st>>>(hist, nbins, ee);
+    ee_finish_kernel<<<1, 1024, 0, st>>>(hist, nbins, ee);
     return cudaGetLastError();
 }
 

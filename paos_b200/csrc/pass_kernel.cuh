@@ -10,6 +10,8 @@
 // Replaces the array arithmetic of paos/classes/wfo.py:200-201 (make_stop scale), :273-276 (aperture),
 // :359-366 (lens), :462-472 (ptp), :493-509 (stw), :530-545 (wts), :650-652/:867-869/:947 (phase screens).
 #pragma once
+#include <cstdlib>
+
 #include "device_types.h"
 #include "fft_core.cuh"
 
@@ -262,6 +264,11 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
     const C<R>* src = reinterpret_cast<const C<R>*>(P.src);
     C<R>* dst = reinterpret_cast<C<R>*>(P.dst);
 
+    // Programmatic dependent launch: this grid may have been started while its predecessor in the stream (the previous
+    // pass, which wrote the field; the table builder; the stop reduction) was still draining.  Everything above is
+    // index arithmetic; nothing below may run before the predecessors have completed and flushed their writes.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
     // Tiles outside [tile_lo, tile_hi] are blanked by an elliptical aperture somewhere in this pass (the planner
     // works the range out from the apertures' bounding boxes) or are zero on input: such a tile is zero at the end of
     // the pass whatever happens before the mask, so it is neither loaded, transformed nor stored -- the planner
@@ -408,6 +415,8 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
         for (int j = 0; j < E; ++j) v[j] = v[j] * c;
     }
 
+    // let the next kernel of the stream get its CTAs scheduled while this grid stores (it waits for our completion above)
+    asm volatile("griddepcontrol.launch_dependents;");
     if (dst) {  // null: a final read-out, the field itself is not needed any more
 #pragma unroll
         for (int j = 0; j < E; ++j) {
@@ -452,8 +461,18 @@ cudaError_t launch_pass_t(const PassParams& P0, const void* tw1, const void* tw2
         tiles = (P.tile_hi < N / W - 1 ? P.tile_hi : N / W - 1) - P.tile_base + 1;
         if (tiles <= 0) return cudaSuccess;  // the whole field is (virtually) zero after this pass
     }
-    kern<<<tiles, threads, smem, st>>>(P, reinterpret_cast<const C<R>*>(tw1), reinterpret_cast<const C<R>*>(tw2));
-    return cudaGetLastError();
+    static const bool pdl = getenv("PAOS_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)tiles);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, P, reinterpret_cast<const C<R>*>(tw1), reinterpret_cast<const C<R>*>(tw2));
 }
 
 }  // namespace paosb

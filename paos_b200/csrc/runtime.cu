@@ -1255,7 +1255,10 @@ int paos_encircled_energy(paos_wfo* w, const void* psf_dev, double dx, double dy
     if (!(r_unit > 0) || !(r_max > 0) || !(dx > 0) || !(dy > 0)) return fail(PAOS_ERR_ARG, "dx, dy, r_unit and r_max must be positive");
     int rc = set_device(w);
     if (rc) return rc;
-    if (!w->ee_hist) CU(cudaMalloc((void**)&w->ee_hist, (4096 + 2) * sizeof(double)));
+    if (!w->ee_hist) {
+        CU(cudaMalloc((void**)&w->ee_hist, (4096 + 2) * sizeof(double)));
+        CU(cudaMemsetAsync(w->ee_hist, 0, (4096 + 2) * sizeof(double), w->stream));
+    }
     const double inv_bin = (double)nbins / (r_unit * r_max);
     cudaError_t e = launch_encircled_energy(psf_dev, w->n, w->dtype == PAOS_C128 ? 0 : 1, dx, dy, xc, yc, inv_bin, nbins, w->ee_hist,
                                             ee_dev_out, w->stream);
