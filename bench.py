@@ -24,6 +24,9 @@ METRIC = "2048^2 fp64 PSFs/sec (full surface chain)"
 UNIT = "PSF/s"
 GRID = 2048
 N_WL = 256
+# False: every timed sweep rebuilds the native surface records of every job from its opt_chain dictionary (what a first
+# sweep over fresh jobs pays); --cache-compiled keeps them between sweeps (diagnostic: isolates the device side)
+CACHE_COMPILED = False
 
 
 def build_jobs(world, grid=GRID, n_wl=N_WL):
@@ -200,7 +203,7 @@ def timed_steps(torch, sweep, jobs, stack, host_stack, steps):
     for s in sweep.streams:
         s.wait_event(start)
     for _ in range(steps):
-        sweep.run(jobs, out=stack, host_out=host_stack, cache_compiled=False)
+        sweep.run(jobs, out=stack, host_out=host_stack, cache_compiled=CACHE_COMPILED)
     for s in sweep.streams:
         e = torch.cuda.Event()
         e.record(s)
@@ -336,7 +339,7 @@ def run_ours(args):
             for s_ in sw.streams:
                 s_.wait_event(a)
             for _ in range(steps):
-                sw.run(jobs, out=ring, ee=dict(r_max=8.0, nbins=nb), ee_out=ee_dev, ee_host_out=ee_host, cache_compiled=False)
+                sw.run(jobs, out=ring, ee=dict(r_max=8.0, nbins=nb), ee_out=ee_dev, ee_host_out=ee_host, cache_compiled=CACHE_COMPILED)
             for s_ in sw.streams:
                 e_ = torch.cuda.Event()
                 e_.record(s_)
@@ -476,12 +479,15 @@ def main():
     ap.add_argument("--n-wl", type=int, default=N_WL)
     ap.add_argument("--slots", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--cache-compiled", action="store_true", help="diagnostic: keep the compiled surface records between sweeps")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: re-launch ourselves one rank per GPU (the driver normally does this with torchrun)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29531"), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    global CACHE_COMPILED
+    CACHE_COMPILED = bool(args.cache_compiled)
     claim_stdout()
     if args.impl == "reference":
         return run_reference(args)

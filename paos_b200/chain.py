@@ -57,6 +57,7 @@ class CompiledChain:
         self.nums = []
         self.saved = []
         init_pitch = True  # no surface so far can have changed the pixel pitch (no propagation, no magnification)
+        has_sag = any(item["type"] == "Grid Sag" for item in items)  # only then is the pitch worth tracking
         for i, item in enumerate(items):
             s = self.array[i]
             kind = item["type"]
@@ -65,7 +66,7 @@ class CompiledChain:
             if kind == "Grid Sag" and not init_pitch:
                 # wfo.py:848-862 resamples the map to the pitch *at the surface*, which only the scalar walk knows
                 raise NotImplementedError("Grid Sag behind a propagation or magnification: use the Python driver")
-            if item["ABCDt"].thickness != 0 or item["ABCDt"].M != 1 or item["ABCDs"].M != 1:
+            if has_sag and (item["ABCDt"].thickness != 0 or item["ABCDt"].M != 1 or item["ABCDs"].M != 1):
                 init_pitch = False
             s.type = _TYPES[kind]
             s.is_stop = 1 if item["is_stop"] else 0
