@@ -457,6 +457,47 @@ __global__ void __launch_bounds__(256) ee_hist_kernel(const R* __restrict__ psf,
         if (sh[b] != 0.0) atomicAdd(&hist[b], sh[b]);
 }
 
+// Centred grid (xc = yc = n/2, the WFO's own origin): the pixels (ix, iy), (n-ix, iy), (ix, n-iy), (n-ix, n-iy) share one
+// radius, so one thread adds the four and issues one histogram update: 4x fewer square roots and shared-memory atomics
+// (which are compare-and-swap loops for fp64 and bound this kernel).  Column 0 and row 0 have no mirror image inside the
+// grid and are taken singly; x = 0 and y = 0 are their own images.
+template <typename R>
+__global__ void __launch_bounds__(256) ee_hist_folded_kernel(const R* __restrict__ psf, int n, double dx, double dy, double inv_bin,
+                                                             int nbins, double* __restrict__ hist) {
+    extern __shared__ double sh[];
+    for (int b = threadIdx.x; b <= nbins; b += blockDim.x) sh[b] = 0.0;
+    __syncthreads();
+    const int h = n / 2;
+    // quadrant x >= 0, y >= 0 plus (as "row h" / "column h" of the loop) the unpaired row 0 and column 0
+    for (int qy = blockIdx.x; qy <= h; qy += gridDim.x) {
+        const bool row0 = qy == h;            // extra iteration: the grid's row 0 (y = -h*dy)
+        const int iy = row0 ? 0 : h + qy;
+        const double y = row0 ? -(double)h * dy : (double)qy * dy;
+        for (int qx = threadIdx.x; qx < 256 * ((h + 1 + 255) / 256); qx += blockDim.x) {
+            double v = 0.0, q = 0.0;
+            if (qx <= h) {
+                const bool col0 = qx == h;    // extra iteration: the grid's column 0
+                const int ix = col0 ? 0 : h + qx;
+                const double x = col0 ? -(double)h * dx : (double)qx * dx;
+                q = sqrt(x * x + y * y) * inv_bin;
+                v = (double)psf[(size_t)iy * n + ix];
+                const bool mx = !col0 && qx > 0, my = !row0 && qy > 0;  // mirror images exist and are distinct
+                if (mx) v += (double)psf[(size_t)iy * n + (n - ix)];
+                if (my) v += (double)psf[(size_t)(n - iy) * n + ix];
+                if (mx && my) v += (double)psf[(size_t)(n - iy) * n + (n - ix)];
+            }
+            const int b = q < (double)nbins ? (int)q : nbins;
+            const unsigned peers = __match_any_sync(0xffffffffu, b);
+            double tot = 0.0;
+            for (unsigned rem = peers; rem; rem &= rem - 1) tot += __shfl_sync(peers, v, __ffs(rem) - 1);
+            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1 && tot != 0.0) atomicAdd(&sh[b], tot);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b <= nbins; b += blockDim.x)
+        if (sh[b] != 0.0) atomicAdd(&hist[b], sh[b]);
+}
+
 // one CTA: ee[k] = (hist[0] + ... + hist[k]) / total, total includes the overflow bin; ee[nbins] receives the total.
 // Block-wide scan (5 consecutive bins per thread, 1024 threads >= 4097 bins): a serial loop over global memory cost
 // more than the whole propagation.
@@ -506,8 +547,15 @@ cudaError_t launch_encircled_energy(const void* psf, int n, int real_is_float, d
     // `hist` is all zeros on entry: zeroed at allocation and by ee_finish_kernel after every use
     const int blocks = n < 148 * 4 ? n : 148 * 4;
     const size_t smem = (size_t)(nbins + 1) * sizeof(double);
-    if (real_is_float) ee_hist_kernel<float><<<blocks, 256, smem, st>>>(reinterpret_cast<const float*>(psf), n, dx, dy, xc, yc, inv_bin, nbins, hist);
-    else ee_hist_kernel<double><<<blocks, 256, smem, st>>>(reinterpret_cast<const double*>(psf), n, dx, dy, xc, yc, inv_bin, nbins, hist);
+    if (xc == 0.5 * n && yc == 0.5 * n) {
+        const int fb = n / 2 + 1 < 148 * 4 ? n / 2 + 1 : 148 * 4;
+        if (real_is_float) ee_hist_folded_kernel<float><<<fb, 256, smem, st>>>(reinterpret_cast<const float*>(psf), n, dx, dy, inv_bin, nbins, hist);
+        else ee_hist_folded_kernel<double><<<fb, 256, smem, st>>>(reinterpret_cast<const double*>(psf), n, dx, dy, inv_bin, nbins, hist);
+    } else if (real_is_float) {
+        ee_hist_kernel<float><<<blocks, 256, smem, st>>>(reinterpret_cast<const float*>(psf), n, dx, dy, xc, yc, inv_bin, nbins, hist);
+    } else {
+        ee_hist_kernel<double><<<blocks, 256, smem, st>>>(reinterpret_cast<const double*>(psf), n, dx, dy, xc, yc, inv_bin, nbins, hist);
+    }
     ee_finish_kernel<<<1, 1024, 0, st>>>(hist, nbins, ee);
     return cudaGetLastError();
 }
