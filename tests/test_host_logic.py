@@ -183,3 +183,31 @@ def test_oracle_encircled_energy_of_a_gaussian():
     assert total == pytest.approx(2 * np.pi * sigma**2 / dx**2, rel=1e-6)
     assert np.max(np.abs(ee - (1 - np.exp(-R**2 / (2 * sigma**2))))) < 8e-3  # pixel-centre binning at dx = sigma/20
     assert np.all(np.diff(ee) >= 0)
+
+
+def test_native_compile_refuses_grid_sag_behind_a_propagation(tmp_path):
+    """The native runner prepares a grid-sag screen for the INIT pitch; a Grid Sag surface behind a propagation has to
+    go through the Python driver (chain.py raises NotImplementedError, Sweep catches it)."""
+    import copy
+
+    from paos_b200 import chain as chain_mod
+    from paos_b200 import configs
+
+    job = configs.grid_sag(grid=64, wavelengths=(3.0,), workdir=str(tmp_path))[0]
+    chain_mod.compile_job(job)  # as shipped: the Grid Sag surface sits right behind the stop, at the INIT pitch
+    assert job["_compiled"].array[1].screen_dx == job["pupil_diameter"] * job["zoom"] / 64
+    late = copy.deepcopy(job["opt_chain"][3])
+    late.update(num=5.5, name="Sag2")
+    moved = {k: v for k, v in job["opt_chain"].items()}
+    moved[5.5] = late
+    job2 = dict(job, opt_chain=dict(sorted(moved.items())))
+    job2.pop("_compiled", None)
+    with pytest.raises(NotImplementedError):
+        chain_mod.compile_job(job2)
+
+
+def test_grid_sag_refuses_absurd_padding():
+    from paos_b200.sag import prepare_sag
+
+    with pytest.raises(ValueError):
+        prepare_sag(np.ones((90, 70)), 70, 90, 6e-5, 6e-5, 0.0, 0.0, 256, 0.0172, 0.0172)
