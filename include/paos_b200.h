@@ -213,6 +213,18 @@ int paos_chain_run(paos_wfo *w, double pupil_diameter, double wavelength, double
                    const paos_surface *surfaces, int n_surfaces, paos_snapshot *snapshots, int max_snapshots,
                    int *n_snapshots, paos_snapshot *final_state);
 
+/* ---- the stand-alone polynomial classes (paos/classes/zernike.py:63-109 `Zernike`, :293-317 `cov`, :388-402 `PolyOrthoNorm`) ----
+ * Polynomials at arbitrary points: rho, phi, mask (numpy masked-array convention, may be NULL) are host arrays of npoints
+ * entries; points with rho > 1 or mask != 0 give 0.  norm may be NULL (ones).  nterms <= 64.
+ *   cov_out (nterms x nterms, may be NULL): mean over the unmasked points of Z_i * Z_j (before any transform);
+ *   out (nterms x npoints, may be NULL): the stack, multiplied from the left by the row-major nterms x nterms matrix
+ *   mat when that is not NULL (the Gram-Schmidt matrix of PolyOrthoNorm).
+ * Stateless and synchronous (its own device buffers on `device`); an input-preparation call, not part of the
+ * per-wavelength path. */
+int paos_zernike_points(int device, int nterms, const int *m, const int *n, const double *norm, const double *mat,
+                        const double *rho, const double *phi, const unsigned char *mask, size_t npoints, double *out,
+                        double *cov_out);
+
 /* ---- encircled energy (docs/source/user/aberration/index.rst:47-67; the reference documents it but has no code) ---
  * psf_dev: n*n reals on the handle's device (double for a complex128 handle, float for complex64), e.g. the
  * destination of paos_wfo_read_device(PAOS_READ_PSF).  Pixel (ix, iy) sits at x = (ix - xc)*dx, y = (iy - yc)*dy

@@ -14,5 +14,5 @@ from .abcd import ABCD  # noqa: F401
 from .coordinate_break import coordinate_break  # noqa: F401
 from .wfo import WFO  # noqa: F401
 from .run import run, push_results  # noqa: F401
-from .zernike import j2mn, mn2j  # noqa: F401
+from .zernike import PolyOrthoNorm, Zernike, j2mn, mn2j  # noqa: F401
 from .parse_config import parse_config  # noqa: F401

@@ -73,6 +73,7 @@ SIGNATURES = {
     "paos_wfo_materialize": (_i, [_vp]),
     "paos_wfo_read_device_final": (_i, [_vp, _i, _vp]),
     "paos_chain_run": (_i, [_vp, _d, _d, _d, _d, _d, _vp, _i, _vp, _i, C.POINTER(C.c_int), _vp]),
+    "paos_zernike_points": (_i, [_i, _i, _ip, _ip, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp]),
     "paos_encircled_energy": (_i, [_vp, _vp, _d, _d, _d, _d, _d, _d, _i, _vp]),
     "paos_wfo_stats": (_i, [_vp, C.POINTER(PaosStats)]),
     "paos_wfo_enable_timing": (_i, [_vp, _i]),

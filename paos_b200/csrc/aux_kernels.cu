@@ -283,6 +283,88 @@ cudaError_t launch_zernike(const ZernParams& Z, const unsigned char* mask, doubl
     return cudaGetLastError();
 }
 
+// ---- Zernike polynomials at arbitrary points (the stand-alone class, zernike.py:63-109) ---------------------------------
+// stack[k][p] = norm_k * R_k(rho_p) * ang_k(phi_p); 0 where the point is masked (rho > 1 or mask[p]).  Z.coef carries
+// norm * binom * (-1)^k as for the screen kernel; cos/sin(|m| phi) by repeated rotation of (cos phi, sin phi).
+__global__ void __launch_bounds__(256) zernike_points_kernel(const __grid_constant__ ZernParams Z, const double* __restrict__ rho,
+                                                             const double* __restrict__ phi, const unsigned char* __restrict__ mask,
+                                                             size_t npoints, double* __restrict__ out) {
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npoints; p += (size_t)gridDim.x * blockDim.x) {
+        const double r = rho[p];
+        if (r > 1.0 || (mask && mask[p])) {
+            for (int k = 0; k < Z.K; ++k) out[(size_t)k * npoints + p] = 0.0;
+            continue;
+        }
+        double s1, c1;
+        sincos(phi[p], &s1, &c1);
+        const double xj = 1.0 - 2.0 * (r * r);
+        for (int k = 0; k < Z.K; ++k) out[(size_t)k * npoints + p] = zern_term(Z, k, r, c1, s1, xj);
+    }
+}
+
+// sums of Z_i * Z_j over all points (masked points hold zeros), one CTA per pair i <= j; CTA `npairs` counts the unmasked
+// points.  Deterministic tree reduction.  out[pair], out[npairs] = count.
+__global__ void __launch_bounds__(256) stack_cov_kernel(const double* __restrict__ stack, const double* __restrict__ rho,
+                                                        const unsigned char* __restrict__ mask, int K, size_t npoints,
+                                                        double* __restrict__ out) {
+    const int npairs = K * (K + 1) / 2;
+    int i = 0, rem = blockIdx.x;
+    const bool counting = (int)blockIdx.x == npairs;
+    if (!counting)
+        while (rem >= K - i) {
+            rem -= K - i;
+            ++i;
+        }
+    const int j = i + rem;
+    double acc = 0.0;
+    for (size_t p = threadIdx.x; p < npoints; p += blockDim.x) {
+        if (counting) acc += (rho[p] > 1.0 || (mask && mask[p])) ? 0.0 : 1.0;
+        else acc += stack[(size_t)i * npoints + p] * stack[(size_t)j * npoints + p];
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+
+// U[i][p] = sum_j mat[i][j] * Z[j][p] (zernike.py:398-401, the Gram-Schmidt matrix applied to the stack)
+__global__ void __launch_bounds__(256) stack_transform_kernel(const double* __restrict__ stack, const double* __restrict__ mat, int K,
+                                                              size_t npoints, double* __restrict__ out) {
+    extern __shared__ double msh[];  // K*K
+    for (int q = threadIdx.x; q < K * K; q += blockDim.x) msh[q] = mat[q];
+    __syncthreads();
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npoints; p += (size_t)gridDim.x * blockDim.x) {
+        double z[ZERN_MAX];
+        for (int j = 0; j < K; ++j) z[j] = stack[(size_t)j * npoints + p];
+        for (int i = 0; i < K; ++i) {
+            double acc = 0.0;
+            for (int j = 0; j < K; ++j) acc += msh[i * K + j] * z[j];
+            out[(size_t)i * npoints + p] = acc;
+        }
+    }
+}
+
+cudaError_t launch_zernike_points(const ZernParams& Z, const double* rho, const double* phi, const unsigned char* mask,
+                                  size_t npoints, double* out, cudaStream_t st) {
+    const int blocks = (int)((npoints + 255) / 256 < 148 * 8 ? (npoints + 255) / 256 : 148 * 8);
+    zernike_points_kernel<<<blocks, 256, 0, st>>>(Z, rho, phi, mask, npoints, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_stack_cov(const double* stack, const double* rho, const unsigned char* mask, int K, size_t npoints, double* out,
+                             cudaStream_t st) {
+    stack_cov_kernel<<<K * (K + 1) / 2 + 1, 256, 0, st>>>(stack, rho, mask, K, npoints, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_stack_transform(const double* stack, const double* mat, int K, size_t npoints, double* out, cudaStream_t st) {
+    const int blocks = (int)((npoints + 255) / 256 < 148 * 8 ? (npoints + 255) / 256 : 148 * 8);
+    stack_transform_kernel<<<blocks, 256, (size_t)K * K * sizeof(double), st>>>(stack, mat, K, npoints, out);
+    return cudaGetLastError();
+}
+
 // ---- Zernike covariance (zernike.py:293-317): sums of Z_i*Z_j over the unmasked pixels ---------------------
 // One CTA walks over tiles of COV_TILE pixels: every polynomial of every pixel of the tile goes to shared memory,
 // then each thread accumulates the dot products of the (i <= j) pairs it owns.  Per-CTA partial sums (and the

@@ -10,6 +10,11 @@ cudaError_t launch_zero_outside_band(void* field, int n, int dtype, int axis, in
 cudaError_t launch_readout(const void* src, int n, int dtype, int what, void* out, cudaStream_t st);
 cudaError_t launch_zernike(const ZernParams& Z, const unsigned char* mask, double* out, cudaStream_t st);
 cudaError_t launch_zernike_cov(const ZernParams& Z, const unsigned char* mask, double* partial, int blocks, cudaStream_t st);
+cudaError_t launch_zernike_points(const ZernParams& Z, const double* rho, const double* phi, const unsigned char* mask,
+                                  size_t npoints, double* out, cudaStream_t st);
+cudaError_t launch_stack_cov(const double* stack, const double* rho, const unsigned char* mask, int K, size_t npoints, double* out,
+                             cudaStream_t st);
+cudaError_t launch_stack_transform(const double* stack, const double* mat, int K, size_t npoints, double* out, cudaStream_t st);
 cudaError_t launch_real_to_complex(const double* src, int n, int dtype, void* dst, cudaStream_t st);
 cudaError_t launch_psd_finalize(const void* f, int n, int dtype, const double* noise2, double SR, double unit,
                                 double* out, cudaStream_t st);

@@ -609,6 +609,17 @@ static int resolve_timing(paos_wfo* w) {
     return PAOS_OK;
 }
 
+// RAII for the temporaries of the stateless entry points (paos_zernike_points)
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+
 // ---------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------
@@ -998,12 +1009,12 @@ static double binom(int n, int k) {
 }
 
 // fill the kernel parameters of one chunk of <= ZERN_MAX terms; coef_in may be NULL (coefficient 1)
-static int fill_zern(paos_wfo* w, ZernParams& Z, int s, int nterms, const int* m, const int* n, const double* coef_in,
+static int fill_zern(int grid_n, ZernParams& Z, int s, int nterms, const int* m, const int* n, const double* coef_in,
                      const double* norm_in, double radius, double dx, double dy, double offset, int origin) {
     Z = ZernParams{};
     Z.K = std::min(ZERN_MAX, nterms - s);
     Z.origin = origin;
-    Z.n = w->n;
+    Z.n = grid_n;
     Z.accumulate = s > 0;
     Z.radius = radius;
     Z.dx = dx;
@@ -1049,7 +1060,7 @@ int paos_wfo_zernike_masked(paos_wfo* w, int nterms, const int* m, const int* n,
     if ((rc = upload_mask(w, host_mask, &dmask))) return rc;
     for (int s = 0; s < nterms; s += ZERN_MAX) {
         ZernParams Z;
-        if ((rc = fill_zern(w, Z, s, nterms, m, n, coef, nullptr, radius, dx, dy, offset, origin))) return rc;
+        if ((rc = fill_zern(w->n, Z, s, nterms, m, n, coef, nullptr, radius, dx, dy, offset, origin))) return rc;
         cudaError_t e = launch_zernike(Z, dmask, screen, w->stream);
         if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "zernike launch failed: %s", cudaGetErrorString(e));
         w->stats.kernel_launches++;
@@ -1075,7 +1086,7 @@ int paos_zernike_cov(paos_wfo* w, int nterms, const int* m, const int* n, const 
     int rc = set_device(w);
     if (rc) return rc;
     ZernParams Z;
-    if ((rc = fill_zern(w, Z, 0, nterms, m, n, nullptr, norm, radius, dx, dy, offset, origin))) return rc;
+    if ((rc = fill_zern(w->n, Z, 0, nterms, m, n, nullptr, norm, radius, dx, dy, offset, origin))) return rc;
     unsigned char* dmask;
     if ((rc = upload_mask(w, host_mask, &dmask))) return rc;
     const int K = nterms, per = K * K + 1;
@@ -1248,6 +1259,66 @@ int paos_wfo_fft2(paos_wfo* w, int inverse) {
 }
 
 // ---- statistics ----------------------------------------------------------------------------------
+int paos_zernike_points(int device, int nterms, const int* m, const int* n, const double* norm, const double* mat, const double* rho,
+                        const double* phi, const unsigned char* mask, size_t npoints, double* out, double* cov_out) {
+    if (!m || !n || !rho || !phi) return fail(PAOS_ERR_ARG, "null argument");
+    if (!out && !cov_out) return fail(PAOS_ERR_ARG, "nothing to compute: out and cov_out are both null");
+    if (nterms < 1 || nterms > ZERN_MAX) return fail(PAOS_ERR_ARG, "1..%d polynomials per call", ZERN_MAX);
+    if (npoints == 0) return PAOS_OK;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(PAOS_ERR_CUDA, "no CUDA device: libpaos_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return fail(PAOS_ERR_ARG, "device %d out of range (%d devices)", device, count);
+    CU(cudaSetDevice(device));
+    ZernParams Z;
+    int rc = fill_zern(0, Z, 0, nterms, m, n, nullptr, norm, 1.0, 1.0, 1.0, 0.0, 0);
+    if (rc) return rc;
+    const size_t K = (size_t)nterms, vec = npoints * sizeof(double);
+    DevBuf d_rho, d_phi, d_mask, d_stack, d_out, d_mat, d_cov;
+    CU(d_rho.alloc(vec));
+    CU(d_phi.alloc(vec));
+    CU(d_stack.alloc(K * vec));
+    CU(cudaMemcpy(d_rho.p, rho, vec, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_phi.p, phi, vec, cudaMemcpyHostToDevice));
+    if (mask) {
+        CU(d_mask.alloc(npoints));
+        CU(cudaMemcpy(d_mask.p, mask, npoints, cudaMemcpyHostToDevice));
+    }
+    cudaError_t e = launch_zernike_points(Z, d_rho.as<double>(), d_phi.as<double>(), mask ? d_mask.as<unsigned char>() : nullptr, npoints,
+                                          d_stack.as<double>(), nullptr);
+    if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "zernike launch failed: %s", cudaGetErrorString(e));
+    if (cov_out) {
+        const int npairs = nterms * (nterms + 1) / 2;
+        CU(d_cov.alloc((size_t)(npairs + 1) * sizeof(double)));
+        e = launch_stack_cov(d_stack.as<double>(), d_rho.as<double>(), mask ? d_mask.as<unsigned char>() : nullptr, nterms, npoints,
+                             d_cov.as<double>(), nullptr);
+        if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "covariance launch failed: %s", cudaGetErrorString(e));
+        std::vector<double> sums((size_t)npairs + 1);
+        CU(cudaMemcpy(sums.data(), d_cov.p, sums.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        const double cnt = sums[(size_t)npairs];
+        if (!(cnt > 0)) return fail(PAOS_ERR_STATE, "every point is masked: the covariance is undefined");
+        size_t q = 0;
+        for (int i = 0; i < nterms; ++i)
+            for (int j = i; j < nterms; ++j, ++q) cov_out[(size_t)i * nterms + j] = cov_out[(size_t)j * nterms + i] = sums[q] / cnt;
+    }
+    if (out) {
+        const double* src = d_stack.as<double>();
+        if (mat) {
+            CU(d_mat.alloc(K * K * sizeof(double)));
+            CU(d_out.alloc(K * vec));
+            CU(cudaMemcpy(d_mat.p, mat, K * K * sizeof(double), cudaMemcpyHostToDevice));
+            e = launch_stack_transform(d_stack.as<double>(), d_mat.as<double>(), nterms, npoints, d_out.as<double>(), nullptr);
+            if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "stack transform launch failed: %s", cudaGetErrorString(e));
+            src = d_out.as<double>();
+        }
+        CU(cudaMemcpy(out, src, K * vec, cudaMemcpyDeviceToHost));
+    }
+    CU(cudaDeviceSynchronize());
+    return PAOS_OK;
+}
+
 int paos_encircled_energy(paos_wfo* w, const void* psf_dev, double dx, double dy, double xc, double yc, double r_unit,
                           double r_max, int nbins, double* ee_dev_out) {
     if (!w || !psf_dev || !ee_dev_out) return fail(PAOS_ERR_ARG, "null argument");
