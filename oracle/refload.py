@@ -136,6 +136,7 @@ def load():
     ns.coordinate_break = importlib.import_module("paos.core.coordinateBreak").coordinate_break
     ns.parse_config = importlib.import_module("paos.core.parseConfig").parse_config
     ns.run = importlib.import_module("paos.core.run").run
+    ns.raytrace = importlib.import_module("paos.core.raytrace").raytrace
     ns.Material = importlib.import_module("paos.util.material").Material
     ns.units = sys.modules["astropy.units"]
     return ns

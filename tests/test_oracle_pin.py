@@ -10,6 +10,7 @@ import golden_cases as gc
 from oracle import paos_np, refload
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # same machine, same numpy: bit-equal in practice; the tolerance allows for a different libm / pocketfft build
 TOL = 1e-12
 
@@ -166,3 +167,17 @@ def test_grid_sag_resampling_control_flow_equals_reference(ny, nx, pitch, xdec, 
         assert seen == calls
     assert ra.shape == (64, 64)
     assert np.array_equal(a._wfo, b._wfo) and np.array_equal(ra.filled(0), rb.filled(0)) and np.array_equal(ra.mask, rb.mask)
+
+
+@needs_reference
+@pytest.mark.parametrize("name,field", [("Hubble_simple.ini", None), ("Ariel_AIRS-CH0.ini", {"us": 1e-3, "ut": -2e-3})])
+def test_raytrace_equals_reference(name, field):
+    """paos_b200.raytrace (host scalars) against the unmodified paos.core.raytrace on the same parsed chains."""
+    import paos_b200
+
+    ref = refload.load()
+    path = os.path.join(ROOT, "paos_b200", "lens_data", name)
+    _, _, _, fields_r, chains_r = ref.parse_config(path)
+    _, _, _, fields_p, chains_p = paos_b200.parse_config(path)
+    f = field or fields_r[0]
+    assert ref.raytrace(f, chains_r[0], x=0.01, y=-0.02) == paos_b200.raytrace(field or fields_p[0], chains_p[0], x=0.01, y=-0.02)
