@@ -17,3 +17,4 @@ from .run import run, push_results  # noqa: F401
 from .zernike import PolyOrthoNorm, Zernike, j2mn, mn2j  # noqa: F401
 from .parse_config import parse_config  # noqa: F401
 from .raytrace import raytrace  # noqa: F401
+from .pipeline import pipeline  # noqa: F401

@@ -272,3 +272,23 @@ def test_sweep_grid_sag_behind_a_change_of_sampling(tmp_path):
     last = ref[max(ref)]
     assert relerr(out[0].cpu().numpy(), last["amplitude"]) <= TOL["complex128"]
     assert meta[0]["dx"] == last["dx"]
+
+
+def test_pipeline_front_end_returns_the_reference_dictionaries():
+    """paos_b200.pipeline(passvalue) with return=True: one run() dictionary per wavelength of the lens file."""
+    import os
+
+    import paos_b200
+    from oracle import paos_np
+
+    conf = os.path.join(os.path.dirname(paos_b200.__file__), "lens_data", "Hubble_simple.ini")
+    out = paos_b200.pipeline({"conf": conf, "save": False, "return": True, "light_output": True, "debug": True})
+    pup, params, wls, fields, chains = paos_b200.parse_config(conf)
+    assert len(out) == len(wls)
+    for got, wl, chain in zip(out, wls, chains):
+        for item in chain.values():
+            item["save"] = item["name"] == "IMAGE_PLANE"
+        ref = paos_np.run(pup, 1e-6 * wl, params["grid_size"], params["zoom"], fields[0], chain)
+        assert sorted(got) == sorted(ref) and len(ref) == 1
+        compare(got, ref, TOL["complex128"])
+    assert paos_b200.pipeline({"conf": conf, "save": False}) is None

@@ -211,3 +211,27 @@ def test_grid_sag_refuses_absurd_padding():
 
     with pytest.raises(ValueError):
         prepare_sag(np.ones((90, 70)), 70, 90, 6e-5, 6e-5, 0.0, 0.0, 256, 0.0172, 0.0172)
+
+
+def test_pipeline_chain_setup_and_refusals():
+    """paos_b200.pipeline's option handling (pipeline.py:88-129): light_output keeps only IMAGE_PLANE, the -wfe option
+    overrides Z1 with column c + 4 of the realization table; save / plot requests are refused, not dropped."""
+    import paos_b200
+    from paos_b200 import configs
+
+    pl = sys.modules["paos_b200.pipeline"]  # the package re-exports the function under the module's name, like the reference
+    conf = os.path.join(ROOT, "paos_b200", "lens_data", "Ariel_FGS-FGS1.ini")
+    csv = os.path.join(ROOT, "paos_b200", "lens_data", "wfe_realization_SN20210914.csv")
+    pup, params, wls, field, chains = pl.setup_chains({"conf": conf, "light_output": True, "wfe": f"{csv},7"})
+    assert len(chains) == len(wls) and field == paos_b200.parse_config(conf)[3][0]
+    for chain in chains:
+        saved = [it["name"] for it in chain.values() if it["save"]]
+        assert saved == ["IMAGE_PLANE"]
+        for it in chain.values():  # Z1 is 'ignore = True' in the shipped file: the override is dead unless it is enabled
+            assert it["name"] != "Z1"
+    want = np.append(np.zeros(3), configs.wfe_table()[:, 3 + 7] * 1e-9)
+    assert np.array_equal(np.append(np.zeros(3), pl.read_wfe_column(csv, "7")), want) and len(want) == 36
+    with pytest.raises(NotImplementedError):
+        paos_b200.pipeline({"conf": conf})  # save defaults to True, as in the reference
+    with pytest.raises(NotImplementedError):
+        paos_b200.pipeline({"conf": conf, "save": False, "plot": True})
