@@ -428,8 +428,6 @@ class WFO:
             seed=None, return_wfe=True):
         """PSD + roughness screen (``wfo.py:873-949``).  ``noise=(n1, n2)`` injects the two standard-normal
         draws of ``psd.py:113,:142`` (bit-parity mode); otherwise they are drawn on the device from ``seed``."""
-        import ctypes as ct
-
         f_nyq = 0.5 * np.sqrt(self._dx**-2 + self._dy**-2)
         if fmax is None:
             fmax = f_nyq
@@ -437,6 +435,15 @@ class WFO:
             assert fmax <= f_nyq, f"fmax must be less than or equal to f_Nyq ({f_nyq})"
         if fmin is None:
             fmin = 1 / (self._n * np.max([self._dx, self._dy]))
+        wfe = self._psd_screen(A, B, C, fknee, fmin, fmax, SR, units, noise, seed, return_wfe)
+        if not return_wfe:
+            return None
+        return np.ma.masked_array(wfe, mask=np.zeros((self._n, self._n), dtype=bool))
+
+    def _psd_screen(self, A, B, C, fknee, fmin, fmax, SR, units, noise, seed, return_wfe=True):
+        """``paos_wfo_psd`` at the current pitch: multiplies the wavefront by the screen and returns it (ndarray) if asked."""
+        import ctypes as ct
+
         scale = 1.0 if units is None else _unit_to_m(units)
         n1 = n2 = None
         if noise is not None:
@@ -452,9 +459,7 @@ class WFO:
             n1.ctypes.data_as(ct.c_void_p) if n1 is not None else None,
             n2.ctypes.data_as(ct.c_void_p) if n2 is not None else None,
             ct.c_uint64(int(seed)), wfe.ctypes.data_as(ct.c_void_p) if return_wfe else None))
-        if not return_wfe:
-            return None
-        return np.ma.masked_array(wfe, mask=np.zeros((self._n, self._n), dtype=bool))
+        return wfe
 
     # ---- test helper ------------------------------------------------------------------------------
     def _fft2(self, inverse=False):

@@ -81,3 +81,46 @@ def test_constructor_errors():
         paos_b200.Zernike(0, rho, phi)
     with pytest.raises(ValueError):
         paos_b200.Zernike(65, rho, phi)
+
+
+def _psd_case(grid=256):
+    phi_x, phi_y, zoom = 110.0, 73.0, 4
+    delta = zoom * max(phi_x, phi_y) / grid
+    x = np.arange(-grid // 2, grid // 2) * delta
+    xx, yy = np.meshgrid(x, x)
+    inside = (2 * xx / phi_x) ** 2 + (2 * yy / phi_y) ** 2 <= 1
+    pupil = np.ma.masked_array(inside.astype(float), mask=~inside)
+    fx = np.fft.fftfreq(grid, delta)
+    fxx, fyy = np.meshgrid(fx, fx)
+    f = np.sqrt(fxx**2 + fyy**2)
+    f[f == 0] = 1e-100
+    return pupil, f
+
+
+def test_psd_class_with_injected_noise_matches_oracle():
+    """paos_b200.PSD (the docstring example of paos/classes/psd.py:44-66) against the oracle's screen for the same draws."""
+    import paos_b200
+    from oracle import paos_np
+
+    pupil, f = _psd_case()
+    rng = np.random.default_rng(12)
+    n1, n2 = rng.standard_normal(pupil.shape), rng.standard_normal(pupil.shape)
+    args = dict(A=7.0, B=0.0, C=1.5, fknee=1.0, fmin=1 / 20, fmax=1 / 2, SR=0.3)
+    got = paos_b200.PSD(pupil, f=f, units="nm", noise=(n1, n2), **args)()
+    ref = paos_np.psd_screen(pupil.shape, f, unit_to_m=1e-9, noise1=n1, noise2=n2, **args)
+    assert np.array_equal(np.ma.getmaskarray(got), np.ma.getmaskarray(pupil))
+    assert np.max(np.abs(got.data - ref.data)) <= 1e-11 * np.max(np.abs(ref.data))
+
+
+def test_psd_class_statistics_and_refusals():
+    import paos_b200
+
+    pupil, f = _psd_case(512)
+    args = dict(A=7.0, B=0.0, C=1.5, fknee=1.0, fmin=1 / 20, fmax=1 / 2)
+    wfe = paos_b200.PSD(pupil, f=f, SR=0.0, units="nm", seed=5, **args)()
+    want = 2 * paos_b200.PSD.sfe_rms(7.0, 0.0, 1.5, 1.0, 1 / 20, 1 / 2) * 1e-9  # WFE = 2 x SFE
+    assert np.std(wfe.data) == pytest.approx(want, rel=0.15)
+    with pytest.raises(NotImplementedError):
+        paos_b200.PSD(np.ones((100, 100)), f=np.ones((100, 100)), fmin=0.1, fmax=1.0)
+    with pytest.raises(NotImplementedError):
+        paos_b200.PSD(pupil, f=f * np.linspace(1, 2, 512)[None, :], fmin=0.1, fmax=1.0)
