@@ -292,3 +292,38 @@ def test_pipeline_front_end_returns_the_reference_dictionaries():
         assert sorted(got) == sorted(ref) and len(ref) == 1
         compare(got, ref, TOL["complex128"])
     assert paos_b200.pipeline({"conf": conf, "save": False}) is None
+
+
+def _shipped_lens_files():
+    import os
+
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "paos_b200", "lens_data")
+    return sorted(f for f in os.listdir(d) if f.endswith(".ini") and f != "test_Grid_Sag.ini")
+
+
+@pytest.mark.parametrize("name", _shipped_lens_files())
+def test_every_shipped_lens_file_chain_parity(name):
+    """First wavelength of every optical system the reference ships (13 lens files; the grid-sag one has its own test) on a
+    128^2 grid: device run against the oracle's run -- which tests/test_oracle_pin.py holds bit-identical to the unmodified
+    reference on the same files -- at every saved surface; where the reference refuses (fmax > f_Nyq on a small grid), so
+    does the device path."""
+    import os
+
+    import paos_b200
+    from oracle import paos_np
+
+    path = os.path.join(os.path.dirname(paos_b200.__file__), "lens_data", name)
+    pup, params, wls, fields, chains = paos_b200.parse_config(path)
+    args = (pup, 1e-6 * wls[0], 128, params["zoom"], fields[0], chains[0])
+    np.random.seed(3)
+    try:
+        ref = paos_np.run(*args, unit_to_m=lambda u: u.to(type(u)("m")))
+    except AssertionError:
+        with pytest.raises(AssertionError):
+            paos_b200.run(*args)
+        return
+    has_psd = any(it["type"] == "PSD" for it in chains[0].values())
+    if has_psd:
+        pytest.skip("PSD screens need injected noise for parity (covered by test_ta_ground_psd_injected_noise)")
+    got = paos_b200.run(*args)
+    compare(got, ref, TOL["complex128"])
