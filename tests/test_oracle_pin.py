@@ -257,3 +257,52 @@ def test_every_lens_file_of_the_reference_parses_identically(name, monkeypatch):
         for key in ("dx", "dy", "wz", "distancetofocus", "fratio", "wl", "propagator"):
             va, vb = rr[num][key], ro[num][key]
             assert va == vb or (np.isnan(va) and np.isnan(vb)), (name, num, key)
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", range(12))
+def test_random_call_sequences_equal_reference(seed):
+    """Random sequences of WFO calls with random parameters (apertures and obscurations of both shapes, lenses of either sign,
+    propagations through every II / IO / OI / OO branch, magnifications, media, Zernike screens): oracle and unmodified
+    reference stay bit-identical in the array and in every pilot-beam scalar, and raise the same exceptions."""
+    ref = refload.load()
+    rng = np.random.default_rng(100 + seed)
+    n = 64
+    D, wl, zoom = rng.uniform(0.5, 2.0), rng.uniform(0.5e-6, 8e-6), int(rng.choice([1, 2, 4]))
+    a, b = ref.WFO(D, wl, n, zoom), paos_np.WFO(D, wl, n, zoom)
+    scalars = ("wl", "z", "w0", "zw0", "zr", "dx", "dy", "C", "fratio", "wz", "distancetofocus")
+    for step in range(14):
+        kind = rng.choice(["aperture", "lens", "propagate", "magnify", "medium", "zernike", "stop"])
+        d = a.dx
+        if kind == "aperture":
+            kw = dict(shape=str(rng.choice(["elliptical", "rectangular"])), obscuration=bool(rng.random() < 0.3))
+            call = ("aperture", (rng.normal() * 3 * d, rng.normal() * 3 * d), dict(hx=rng.uniform(4, 30) * d, hy=rng.uniform(4, 30) * a.dy, **kw))
+        elif kind == "lens":
+            call = ("lens", (float(rng.choice([-1, 1]) * 10 ** rng.uniform(-1, 1.5)),), {})
+        elif kind == "propagate":
+            call = ("propagate", (float(10 ** rng.uniform(-3, 1.5)),), {})
+        elif kind == "magnify":
+            call = ("Magnification", (rng.uniform(0.5, 2.0), rng.uniform(0.5, 2.0)), {})
+        elif kind == "medium":
+            call = ("ChangeMedium", (float(rng.choice([1.0, 1.5, 1 / 1.5, -1.0])),), {})
+        elif kind == "zernike":
+            K = int(rng.integers(4, 22))
+            call = ("zernikes", (np.arange(K), rng.normal(size=K) * 30e-9, str(rng.choice(["ansi", "standard", "noll", "fringe"]))),
+                    dict(normalize=bool(rng.random() < 0.5), radius=float(rng.uniform(5, 25) * d), origin=str(rng.choice(["x", "y"]))))
+        else:
+            call = ("make_stop", (), {})
+        results = []
+        for w in (a, b):
+            try:
+                getattr(w, call[0])(*call[1], **call[2])
+                results.append(None)
+            except (ValueError, AssertionError, ZeroDivisionError, KeyError) as e:
+                # KeyError: zernike.py:100-104 builds the angular functions up to m.max() only, so a truncation whose
+                # largest |m| occurs with a negative sign alone (e.g. 4 ANSI terms) crashes in the reference; the oracle
+                # restates that, the device path evaluates such series (DESIGN.md section 4)
+                results.append(type(e))
+        assert results[0] == results[1], (step, call[0], results)
+        assert np.array_equal(a._wfo, b._wfo, equal_nan=True), (step, call[0])
+        for k in scalars:
+            va, vb = getattr(a, k), getattr(b, k)
+            assert va == vb or (np.isnan(va) and np.isnan(vb)), (step, call[0], k, va, vb)
