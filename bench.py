@@ -47,19 +47,90 @@ def build_jobs(world, grid=GRID, n_wl=N_WL):
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU arm: the reference's numpy algorithm (oracle port) over the host cores
+# CPU arm: the reference's own implementation of the path on the host cores.
+#
+# Preferred: the UNMODIFIED reference modules (``/root/reference`` in the build container, the byte-identical copy staged by
+# ``tools/stage_ref.py`` under the git-ignored ``oracle/_ref/`` on the GPU box) through the reference's own public API --
+# ``parse_config`` on a lens file, then ``run`` -- loaded by ``oracle/refload.py``: ``kind = "reference"``.  Fallback when
+# no copy is present: the numpy port ``oracle/paos_np.py`` (bit-identical to the reference on the same numpy): "port".
+# Neither the parent nor the workers import ``paos_b200`` (whose __init__ would dlopen the CUDA library).
 # ---------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    grid, n_wl, index = args
-    os.environ["OMP_NUM_THREADS"] = "1"
-    from oracle import paos_np
-    from paos_b200 import configs
+LENS_FILE = os.path.join(ROOT, "paos_b200", "lens_data", "Ariel_AIRS-CH0.ini")
 
-    job = configs.airs_ch0(grid=grid, n_wl=n_wl)[index]
-    t0 = time.perf_counter()
-    res = paos_np.run(job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"], job["opt_chain"])
-    amp = res[max(res.keys())]["amplitude"]
-    return time.perf_counter() - t0, float((amp**2).sum())
+
+def sweep_wavelengths(n_wl):
+    """The sweep of BASELINE.json configs[1] in micron (same expression as paos_b200.configs.airs_ch0)."""
+    import numpy as np
+
+    return np.linspace(1.95, 3.9, n_wl) if n_wl > 1 else np.array([1.95])
+
+
+def cpu_kind():
+    from oracle import refload
+
+    return "reference" if refload.reference_available() else "port"
+
+
+def _host_only_configs():
+    """paos_b200.configs without running paos_b200/__init__.py (pure host-side parsing; no dlopen of the CUDA library)."""
+    import importlib
+    import types
+
+    if "paos_b200" not in sys.modules:
+        pkg = types.ModuleType("paos_b200")
+        pkg.__path__ = [os.path.join(ROOT, "paos_b200")]
+        sys.modules["paos_b200"] = pkg
+    return importlib.import_module("paos_b200.configs")
+
+
+def _cpu_worker(args):
+    """One chain of the sweep on one core.  Returns (seconds, path of the saved IMAGE_PLANE amplitude or None)."""
+    grid, n_wl, index, ut, keep_dir = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import numpy as np
+
+    from oracle import refload
+
+    wl_um = float(sweep_wavelengths(n_wl)[index])
+    field = {"us": 0.0, "ut": float(ut)}
+    if refload.reference_available():
+        import configparser
+        import tempfile
+
+        ref = refload.load()
+        cfg = configparser.ConfigParser()
+        cfg.read(LENS_FILE)
+        cfg["general"]["grid_size"] = str(grid)
+        for key in list(cfg["wavelengths"]):
+            del cfg["wavelengths"][key]
+        cfg["wavelengths"]["w1"] = repr(wl_um)
+        with tempfile.NamedTemporaryFile("w", suffix=".ini", delete=False) as fh:
+            cfg.write(fh)
+            path = fh.name
+        try:
+            pup, params, wls, fields, chains = ref.parse_config(path)
+        finally:
+            os.unlink(path)
+        chain = chains[0]
+        for item in chain.values():  # pipeline.py:112-115 light_output: keep the IMAGE_PLANE snapshot only
+            item["save"] = item["name"] == "IMAGE_PLANE"
+        f0 = dict(fields[0])
+        f0["ut"] = f0["ut"] + field["ut"]
+        t0 = time.perf_counter()
+        res = ref.run(pup, 1.0e-6 * wls[0], params["grid_size"], params["zoom"], f0, chain)
+    else:
+        from oracle import paos_np
+
+        job = _host_only_configs().airs_ch0(grid=grid, n_wl=n_wl)[index]
+        f0 = {"us": job["field"]["us"], "ut": job["field"]["ut"] + field["ut"]}
+        t0 = time.perf_counter()
+        res = paos_np.run(job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], f0, job["opt_chain"])
+    dt = time.perf_counter() - t0
+    out = None
+    if keep_dir:
+        out = os.path.join(keep_dir, f"amp_{index}.npy")
+        np.save(out, res[max(res.keys())]["amplitude"])
+    return dt, out
 
 
 def cpu_cores():
@@ -69,13 +140,17 @@ def cpu_cores():
         return os.cpu_count() or 1
 
 
-def cpu_step(pool, procs, grid=GRID, n_wl=N_WL, offset=0):
-    """One bounded CPU sample: `procs` wavelengths of the sweep, one process each.  Returns (PSF/s, seconds)."""
-    idx = [(grid, n_wl, (offset + i * max(1, n_wl // procs)) % n_wl) for i in range(procs)]
+def cpu_chains(pool, indices, grid=GRID, n_wl=N_WL, ut=0.0, keep_dir=None):
+    """Propagate the wavelengths ``indices`` of the sweep over the pool.  Returns (PSF/s, seconds, worker results)."""
     t0 = time.perf_counter()
-    pool.map(_cpu_worker, idx)
+    res = pool.map(_cpu_worker, [(grid, n_wl, int(i), ut, keep_dir) for i in indices], chunksize=1)
     dt = time.perf_counter() - t0
-    return procs / dt, dt
+    return len(indices) / dt, dt, res
+
+
+def spread(count, n_wl, offset=0):
+    """``count`` wavelength indices spread evenly over the sweep."""
+    return [(offset + i * max(1, n_wl // count)) % n_wl for i in range(count)]
 
 
 def make_pool(procs):
@@ -90,30 +165,33 @@ def cpu_procs():
 
 
 def run_reference(args):
+    """The CPU arm as a stand-alone run.  A 2048^2 chain is ~30-50 s of numpy on one core and cannot be made shorter, so
+    the run is sized from a measured chain time: one round (one chain per core) is timed first; it is the warm-up when
+    warm-up steps were asked for.  The timed region is then ONE ``pool.map`` of R rounds (R * procs chains, every core busy
+    throughout) with R chosen so that the whole run stays inside ``PAOS_BENCH_REF_BUDGET_S`` (default 420 s); it is
+    reported as ``steps`` equal steps of R * procs / steps chains each.  PSF/s = chains / wall time does not depend on
+    how the chains are cut into steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    t_start = time.perf_counter()
     procs = cpu_procs()
-    pool = make_pool(procs)
-    # one 2048^2 chain is ~30 s of numpy on one core and cannot be made shorter, so a step (one chain per core) is
-    # ~30 s; the CPU path needs no warm-up, so warm-up steps are capped to keep the run within the time budget
     budget_s = float(os.environ.get("PAOS_BENCH_REF_BUDGET_S", "420"))
-    warm_done = 0
+    kind = cpu_kind()
+    pool = make_pool(procs)
     try:
-        t_est = None
-        for w in range(args.warmup):
-            if t_est is not None and (args.steps + w + 1) * t_est > budget_s:
-                break
-            _, t_est = cpu_step(pool, procs, offset=w)
-            warm_done += 1
-        t0 = time.perf_counter()
-        for k in range(args.steps):
-            cpu_step(pool, procs, offset=args.warmup + k)
-        dt = time.perf_counter() - t0
+        _, t_round, _ = cpu_chains(pool, spread(procs, N_WL, 0))
+        warm_done = 1
+        used = time.perf_counter() - t_start
+        rounds = int(max(1, min(args.steps, (budget_s - used) // (1.1 * t_round))))
+        idx = []
+        for r in range(rounds):
+            idx += spread(procs, N_WL, 1 + r)
+        value, dt, _ = cpu_chains(pool, idx)
     finally:
         pool.close()
         pool.join()
-    value = procs * args.steps / dt
+    n_chains = len(idx)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -121,10 +199,12 @@ def run_reference(args):
         "config": {"workload": f"Ariel_AIRS-CH0.ini {GRID}^2 complex128, {N_WL} wavelengths 1.95-3.9 um per GPU "
                                f"(rank r = field point r), IMAGE_PLANE |.|^2 only",
                    "grid": GRID, "wavelengths_per_gpu": N_WL,
-                   "sample": f"each step propagates {procs} wavelengths spread evenly over that sweep (one per host core); "
+                   "sample": f"{n_chains} wavelengths spread evenly over that sweep, propagated by {procs} host processes in one "
+                             f"pool.map ({rounds} rounds of one chain per core), reported as {args.steps} equal steps; "
                              "PSF/s = wavelengths / wall time"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
-                         "sample": f"{procs} wavelengths per step (one numpy process each), {args.steps} steps, {warm_done} warm-up steps run"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind,
+                         "sample": f"{n_chains} chains in {dt:.1f} s on {procs} cores after {warm_done} untimed round "
+                                   f"({t_round:.1f} s); budget {budget_s:.0f} s, whole run {time.perf_counter() - t_start:.0f} s"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -405,18 +485,60 @@ def run_ours(args):
                             "line FFTs per sweep and lines blanked by an aperture mask are neither loaded nor transformed, so achieved exceeds "
                             "the HBM peak; sweep_GBps = upper bound of the real read+write bytes of the field / time"}
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------------
+    # ---- CPU baseline beside it (rank 0, N = 1 only) + parity of the same wavelengths in the same run -------------
+    # (BASELINE.md 4.4 / SURVEY 8d: max|amp_gpu - amp_ref| / max|amp_ref| <= 1e-10 for complex128, 1e-4 for complex64)
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        import shutil
+        import tempfile
+
         procs = cpu_procs()
+        # the sample: the wavelengths whose chain takes the other propagator route (35 instead of 39 FFT2: different
+        # inside/outside decisions of the pilot beam), then wavelengths spread evenly over the sweep, one per core
+        sw1 = sweep_mod.Sweep(grid, device=local_rank, dtype=args.dtype, slots=1, what="amplitude")
+        nfft2 = []
+        for j in jobs:
+            f0 = sw1.stats()["fft2_recorded"]
+            sw1.run([j], out=stack[:1])
+            nfft2.append(int(sw1.stats()["fft2_recorded"] - f0))
+        common = max(set(nfft2), key=nfft2.count)
+        odd = [i for i, c in enumerate(nfft2) if c != common]
+        sample = odd[:procs]
+        for i in spread(procs, n_wl):
+            if len(sample) < procs and i not in sample:
+                sample.append(i)
+        keep = tempfile.mkdtemp(prefix="paos_bench_cpu_")
         pool = make_pool(procs)
         try:
-            v, dt = cpu_step(pool, procs, grid, n_wl)
+            v, dt, res = cpu_chains(pool, sample, grid, n_wl, keep_dir=keep)
+            tol = 1e-10 if args.dtype == "complex128" else 1e-4
+            amp_gpu, _ = sw1.run([jobs[i] for i in sample], out=stack[: len(sample)])
+            worst, worst_psf, worst_at = 0.0, 0.0, None
+            for k, (i, (_, path)) in enumerate(zip(sample, res)):
+                ref_amp = torch.from_numpy(np.load(path)).to(stack.device)
+                got = amp_gpu[k].to(torch.float64)
+                err = float((got - ref_amp).abs().max() / ref_amp.abs().max())
+                ref_psf = ref_amp * ref_amp
+                err_psf = float((got * got - ref_psf).abs().max() / ref_psf.max())
+                if err > worst:
+                    worst, worst_at = err, i
+                worst_psf = max(worst_psf, err_psf)
+            parity = {"n": len(sample), "worst": worst, "worst_psf": worst_psf, "tolerance": tol, "ok": bool(worst <= tol),
+                      "worst_wavelength_index": worst_at, "fft2_per_psf": {str(c): nfft2.count(c) for c in sorted(set(nfft2))},
+                      "other_route_indices_checked": [i for i in odd if i in sample],
+                      "what": "max|amp_gpu - amp_ref| / max|amp_ref| at IMAGE_PLANE over the cpu_baseline wavelengths "
+                              "(worst_psf: the same for |.|^2), GPU vs the CPU arm's arrays of this run"}
         finally:
             pool.close()
             pool.join()
-        cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
-               "sample": f"{procs} wavelengths of the same sweep, one numpy process per core, {dt:.1f} s wall"}
+            shutil.rmtree(keep, ignore_errors=True)
+        del sw1
+        cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": cpu_kind(),
+               "sample": f"{len(sample)} wavelengths of the same sweep (the {len([i for i in odd if i in sample])} with the other "
+                         f"propagator route + evenly spread ones), one numpy process per core, {dt:.1f} s wall"}
+        if not parity["ok"]:
+            raise SystemExit(f"PARITY FAILURE inside bench.py: {json.dumps(parity)}")
 
     if rank == 0:
         launches = int(st1["kernel_launches"] - st0["kernel_launches"])
@@ -434,7 +556,7 @@ def run_ours(args):
                     "note": "paos_b200.sweep.Sweep.run over host job dicts; inputs are lens-prescription scalars (kernel "
                             "arguments, no array uploads); every PSF (N*N fp64) is copied to pinned host memory inside the timed region"},
             "gpu_launches": launches * world,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
             "host_plan_ms_per_psf": 1e3 * t_host / (len(jobs) * args.steps),
             "fft2_per_step": int(st1["fft2_recorded"] - st0["fft2_recorded"]) // args.steps * world,
             "pass_launches_per_psf": (st1["pass_launches"] - st0["pass_launches"]) / (len(jobs) * args.steps),

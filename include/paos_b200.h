@@ -60,6 +60,8 @@ typedef struct paos_wfo paos_wfo; /* opaque */
 /* ---- library ------------------------------------------------------------------------------- */
 int paos_abi_version(void);
 const char *paos_last_error(void);
+/* "libpaos_b200 sm_100a source <sha1 of csrc/ + include/ + flags> compiled <date>": which tree this binary was made from */
+const char *paos_build_info(void);
 /* sizeof of a public struct as this library was compiled (0: paos_surface, 1: paos_snapshot, 2: paos_stats; -1 for
  * anything else): lets a foreign-function binding check its own mirror of the layout */
 long paos_abi_struct_size(int which);

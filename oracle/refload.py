@@ -1,6 +1,8 @@
 """ORACLE (test infrastructure only) -- stub loader for the UNMODIFIED reference under /root/reference.
 
-Only usable in the build container (``/root/reference`` does not exist on the GPU box).  It registers a
+In the build container it reads ``/root/reference``; on the GPU box, where that tree does not exist, it reads the
+byte-identical copy that ``tools/stage_ref.py`` staged under the git-ignored ``oracle/_ref/`` (checked against its
+sha1 manifest before use).  It registers a
 fake top-level ``paos`` package whose ``__path__`` points into the reference tree (so ``paos/__init__.py``,
 which needs installed metadata and matplotlib, is skipped) and stubs the third-party modules that are
 absent from this image:
@@ -21,11 +23,38 @@ import sys
 import types
 
 REFERENCE_ROOT = "/root/reference"
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 SKIMAGE_CALLS = []  # names of the restated skimage.transform functions the reference has called so far
 
 
+def _staged_ok():
+    """The staged copy is usable only when every file still hashes to what ``tools/stage_ref.py`` recorded."""
+    import hashlib
+    import json
+
+    try:
+        with open(os.path.join(STAGED_ROOT, "MANIFEST.json")) as fh:
+            files = json.load(fh)["files"]
+        for rel, digest in files.items():
+            with open(os.path.join(STAGED_ROOT, rel), "rb") as fh:
+                if hashlib.sha1(fh.read()).hexdigest() != digest:
+                    return False
+        return len(files) > 0
+    except (OSError, ValueError, KeyError):
+        return False
+
+
+def reference_root():
+    """Directory holding the unmodified ``paos`` package: the reference tree, else the staged copy, else None."""
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "paos", "classes")):
+        return REFERENCE_ROOT
+    if _staged_ok():
+        return STAGED_ROOT
+    return None
+
+
 def reference_available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "paos", "classes"))
+    return reference_root() is not None
 
 
 class _Unit:
@@ -62,14 +91,16 @@ def install_stubs():
     """Install the stub modules (idempotent).  Returns the fake ``paos`` package."""
     if "paos" in sys.modules and getattr(sys.modules["paos"], "__oracle_stub__", False):
         return sys.modules["paos"]
-    if not reference_available():
-        raise RuntimeError("reference tree not present; refload is only usable in the build container")
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("neither /root/reference nor a staged copy under oracle/_ref is present (tools/stage_ref.py)")
     from loguru import logger
 
     logger.disable("paos")
 
     pkg = types.ModuleType("paos")
-    pkg.__path__ = [os.path.join(REFERENCE_ROOT, "paos")]
+    pkg.__path__ = [os.path.join(root, "paos")]
+    pkg.__reference_root__ = root
     pkg.logger = logger
     pkg.__author__, pkg.__pkg_name__, pkg.__version__ = "ref", "PAOS", "1.2.12"
     pkg.__oracle_stub__ = True

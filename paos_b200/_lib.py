@@ -45,6 +45,7 @@ _dp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
 SIGNATURES = {
     "paos_abi_version": (_i, []),
     "paos_last_error": (C.c_char_p, []),
+    "paos_build_info": (C.c_char_p, []),
     "paos_device_count": (_i, []),
     "paos_wfo_create": (_i, [C.POINTER(_vp), _i, _i, _i, _vp, _vp]),
     "paos_wfo_destroy": (_i, [_vp]),

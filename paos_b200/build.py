@@ -19,25 +19,51 @@ NVCC_FLAGS = [
 ] + (os.environ.get("PAOS_NVCC_EXTRA", "").split())
 
 
-def _newest_dep():
-    t = 0.0
+INFO = os.path.join(HERE, "build_info.json")
+
+
+def source_hash():
+    """sha1 over every file of csrc/ and include/ plus the compiler flags: what the binary was made from."""
+    import hashlib
+
+    h = hashlib.sha1(" ".join(NVCC_FLAGS).encode())
     for root in (CSRC, os.path.join(HERE, "..", "include")):
-        for f in os.listdir(root):
-            t = max(t, os.path.getmtime(os.path.join(root, f)))
-    return t
+        for f in sorted(os.listdir(root)):
+            h.update(f.encode())
+            with open(os.path.join(root, f), "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()
+
+
+def built_hash():
+    """Source hash recorded next to the shipped library (None when there is no record)."""
+    import json
+
+    try:
+        with open(INFO) as fh:
+            return json.load(fh).get("source_hash")
+    except (OSError, ValueError):
+        return None
 
 
 def build(force=False, verbose=False):
+    """Compile when forced, when the library is missing, or when the sources no longer hash to what the shipped binary
+    records (modification times do not survive a copy to another box).  The hash is also compiled into the library
+    (``paos_build_info()``), so a stale binary cannot pass for a fresh one."""
+    import json
+    import time
+
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_dep():
+    want = source_hash()
+    if not force and os.path.exists(LIB) and built_hash() == want:
         return LIB
     os.makedirs(OBJ, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, f'-DPAOS_SOURCE_HASH="{want}"', "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj + ".log", "w") as fh:
             fh.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
@@ -53,6 +79,10 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    ver = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout.strip().splitlines()
+    with open(INFO, "w") as fh:
+        json.dump({"source_hash": want, "nvcc": ver[-1] if ver else "", "flags": NVCC_FLAGS, "sources": SOURCES,
+                   "built_at": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), "forced": bool(force)}, fh, indent=1)
     return LIB
 
 

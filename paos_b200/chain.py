@@ -118,7 +118,9 @@ class CompiledChain:
                     # upload once and share between jobs that carry the same map (one per wavelength in a sweep)
                     import torch
 
-                    key = (screen.shape, hash(screen[::61, ::53].tobytes()), float(screen.sum()))
+                    import hashlib
+
+                    key = (screen.shape, int(device), hashlib.sha1(screen.tobytes()).hexdigest())
                     cache = screen_cache if screen_cache is not None else {}
                     dev = cache.get(key)
                     if dev is None:
@@ -168,9 +170,13 @@ def compile_job(job, psd_noise=None, device=None, screen_cache=None):
     """Compile (and cache on the job dict) the native surface records of a job.  With ``device`` the grid-sag maps are
     uploaded once (shared through ``screen_cache``) instead of travelling from host memory on every run."""
     cc = job.get("_compiled")
+    sig = (None if device is None else int(device), int(job["gridsize"]), float(job["zoom"]), float(job["pupil_diameter"]))
+    if cc is not None and getattr(cc, "signature", None) != sig:
+        cc = None  # compiled for another GPU (raw device pointers) or another geometry: rebuild
     if cc is None or psd_noise is not None:
         cc = CompiledChain(job["opt_chain"], job["gridsize"], job["pupil_diameter"], job["zoom"],
                            psd_seed=job.get("psd_seed", 0), psd_noise=psd_noise, device=device, screen_cache=screen_cache)
+        cc.signature = sig
         if psd_noise is None:
             job["_compiled"] = cc
     return cc

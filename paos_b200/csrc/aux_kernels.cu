@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) norm2_partial_kernel(const __grid_constan
         for (int g = 0; g < P.ngen; ++g) {
             const GenOp& gg = P.gen[g];
             if (gg.kind == GEN_ELLIPSE && !gg.flag) {
-                const float bq = ((float)iy - (float)gg.p1) * (float)gg.p3;
+                const float bq = (float)((double)iy - gg.p1) * (float)gg.p3;
                 if (bq * bq >= (float)gg.p6 + 1e-5f) blank = true;
             }
         }

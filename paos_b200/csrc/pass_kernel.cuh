@@ -202,7 +202,9 @@ __device__ __forceinline__ void apply_gen(C<R>& v, const GenOp& g, int ix, int i
     switch (g.kind) {
         case GEN_ELLIPSE: {
             // same FP32 interior / exterior classification as the pass kernel; exact routine only in the edge band
-            const float uq = ((float)ix - (float)g.p0) * (float)g.p2, wq = ((float)iy - (float)g.p1) * (float)g.p3;
+            // centre subtracted in double: (float)centre alone would carry up to 1.2e-4 px at n = 4096, more than the margin
+            // allows for semi-axes below ~25 px
+            const float uq = (float)((double)ix - g.p0) * (float)g.p2, wq = (float)((double)iy - g.p1) * (float)g.p3;
             const float r2 = uq * uq + wq * wq;
             double m;
             if (r2 <= (float)g.p5 - 1e-5f) m = 1.0;
@@ -310,16 +312,20 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
                     // p5, p6 = squared radii, in the frame where the ellipse is the unit circle, inside / outside which
                     // a whole pixel is certainly inside / outside; the 1e-5 margins cover the float rounding.  Only
                     // pixels in the thin band between them take the exact (double) routine.
-                    const float cxf = (float)g.p0, cyf = (float)g.p1, sxf = (float)g.p2, syf = (float)g.p3;
+                    // The centre is subtracted in double (two FP64 instructions per thread and mask): (float)centre alone
+                    // would carry up to 1.2e-4 px at n = 4096, i.e. 2.4e-4/a in r^2, more than the margin for a < ~25 px.
+                    // With the difference rounded once, every term below has a relative error of a few 2^-24 and r^2 ~ 1
+                    // at the edge is good to ~5e-7.
+                    const float sxf = (float)g.p2, syf = (float)g.p3;
                     const float in5 = (float)g.p5 - 1e-5f, out6 = (float)g.p6 + 1e-5f;
-                    const float a0 = COL ? ((float)t - cyf) * syf : ((float)t - cxf) * sxf;
+                    const float a0 = COL ? (float)((double)t - g.p1) * syf : (float)((double)t - g.p0) * sxf;
                     const float da = COL ? (float)T * syf : (float)T * sxf;
-                    const float bq = COL ? ((float)line - cxf) * sxf : ((float)line - cyf) * syf;
+                    const float bq = COL ? (float)((double)line - g.p0) * sxf : (float)((double)line - g.p1) * syf;
                     const float b2 = bq * bq;
                     const bool obsc = g.flag != 0;
 #pragma unroll
                     for (int j = 0; j < E; ++j) {
-                        const float aq = a0 + (float)j * da;
+                        const float aq = fmaf((float)j, da, a0);
                         const float r2 = aq * aq + b2;
                         if (r2 <= in5) {
                             if (obsc) v[j] = C<R>((R)0, (R)0);

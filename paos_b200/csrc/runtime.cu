@@ -627,6 +627,10 @@ extern "C" {
 
 int paos_abi_version(void) { return PAOS_ABI_VERSION; }
 const char* paos_last_error(void) { return g_last_error.c_str(); }
+#ifndef PAOS_SOURCE_HASH
+#define PAOS_SOURCE_HASH "unrecorded"
+#endif
+const char* paos_build_info(void) { return "libpaos_b200 sm_100a source " PAOS_SOURCE_HASH " compiled " __DATE__ " " __TIME__; }
 long paos_abi_struct_size(int which) {
     switch (which) {
         case 0: return (long)sizeof(paos_surface);

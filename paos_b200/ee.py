@@ -32,10 +32,16 @@ def encircled_energy(wfo, psf, dx, dy, fratio, wl, r_max=8.0, nbins=256, center=
     if not np.isfinite(fratio):
         raise ValueError("fratio is not finite: the beam has no focus to normalise the radius with")
     xc, yc = (n / 2.0, n / 2.0) if center is None else center
-    if out is None:
+    fresh = out is None
+    if fresh:
         with torch.cuda.stream(wfo._stream):
             out = torch.empty(int(nbins) + 1, dtype=torch.float64, device=psf.device)
     _lib.check(_lib.lib.paos_encircled_energy(
         wfo._handle, C.c_void_p(psf.data_ptr()), float(dx), float(dy), float(xc), float(yc), float(abs(fratio) * wl), float(r_max),
         int(nbins), C.c_void_p(out.data_ptr())))
+    if fresh:
+        # allocated from the WFO stream's pool, consumed on the caller's stream (see WFO._read_device)
+        cur = torch.cuda.current_stream(psf.device)
+        cur.wait_stream(wfo._stream)
+        out.record_stream(cur)
     return out

@@ -126,6 +126,10 @@ class Sweep:
         nslots = len(self.wfos)
         if out.shape[0] < len(jobs) and (ee is None or out.shape[0] % nslots):
             raise ValueError("out is shorter than jobs: only an encircled-energy sweep may use it as a ring, of a multiple of `slots` rows")
+        if host_out is not None and host_out.shape[0] < len(jobs) and host_out.shape[0] % nslots:
+            # rows are written by slot k % nslots: a ring whose length is not a multiple of `slots` would let two slot
+            # streams copy into the same pinned row with no ordering between them
+            raise ValueError("host_out is shorter than jobs: as a ring it must hold a multiple of `slots` rows")
         if ee is not None:
             if self.what != "psf":
                 raise ValueError("encircled energy needs what='psf'")

@@ -146,7 +146,11 @@ class WFO:
         with torch.cuda.stream(self._stream):
             out = torch.empty((self._n, self._n), dtype=tdt, device=self._tdev)
         check(lib.paos_wfo_read_device(self._handle, what, C.c_void_p(out.data_ptr())))
-        torch.cuda.current_stream(self._tdev).wait_stream(self._stream)
+        cur = torch.cuda.current_stream(self._tdev)
+        cur.wait_stream(self._stream)
+        # `out` was allocated from the WFO stream's pool but is consumed on the caller's stream: tell the caching
+        # allocator, or the block could be handed to the next read-out while the caller still has a read pending
+        out.record_stream(cur)
         return out
 
     @property
@@ -417,7 +421,8 @@ class WFO:
     def grid_sag(self, sag, nx, ny, delx, dely, xdec=0.0, ydec=0.0):
         """Grid-sag phase screen (``wfo.py:656-871``).  The map is masked, recentred and padded / cropped on the host
         (``paos_b200/sag.py``, input preparation as in the reference); the phase multiply runs in the fused passes.
-        Maps that would need the reference's skimage resampling raise ``NotImplementedError``."""
+        Maps off the WFO pitch are resampled by ``paos_b200/resample.py``, a restatement of scikit-image 0.24's
+        ``rescale`` / ``resize`` that is not pinned against the library itself (absent from this image)."""
         from .sag import prepare_sag
 
         screen, mask = prepare_sag(sag, int(nx), int(ny), delx, dely, xdec, ydec, self._n, self._dx, self._dy)
