@@ -293,20 +293,31 @@ def timed_steps(torch, sweep, jobs, stack, host_stack, steps):
     return start.elapsed_time(end)
 
 
-def fp64_view(grid, dtype, st0, st1, pass_ms, peaks):
-    """The pipe that actually bounds the pass kernel: FP64 instructions of the butterflies of the
-    lines really transformed / pass-kernel time, against 64 FP64 instructions per clock per SM."""
-    lines = int(st1["lines_transformed"] - st0["lines_transformed"])
-    batches = int(st1["line_ffts_run"] - st0["line_ffts_run"])
-    out = {"lines_transformed": lines, "active_line_fraction": lines / max(batches * grid, 1)}
-    if grid == 2048 and dtype == "complex128" and pass_ms:
-        per_line = 532 * 128  # SASS count of one 2048-point line FFT: 320 DADD + 138 DFMA + 74 DMUL per thread, 128 threads
-        clk = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
-        peak = 64 * 148 * clk
-        out.update({"instr_per_line_fft": per_line, "achieved_Ginstr_s": lines * per_line / (pass_ms * 1e-3) / 1e9,
-                    "peak_Ginstr_s": peak / 1e9, "frac": lines * per_line / (pass_ms * 1e-3) / peak,
-                    "note": "butterflies only (table and mask multiplies not counted); peak = 64 FP64 instr/clk/SM x 148 SMs x max SM clock"})
+# FP64 instructions of one 2048-point complex128 line FFT in the 16 x 8 x 16 form of fft_core.cuh, counted in the SASS of
+# the pass kernel: per thread 320 DADD + 138 DFMA + 74 DMUL = 532 (butterflies and twiddles only: the per-position table
+# multiply, the twiddle products and the mask factors are real work but are NOT counted), 128 threads per line.
+FP64_INSTR_PER_LINE_FFT = {(2048, "complex128"): 532 * 128}
+
+
+def load_peaks():
+    """Measured ceilings: MEASURED_PEAKS.json (driver-written: HBM copy GB/s, max SM clock) and profiles/peaks_r02.json
+    (tools/peaks.cu on this pool's B200: FP64 issue rate, L2 and shared-memory bandwidth)."""
+    out = {}
+    for name in ("MEASURED_PEAKS.json", os.path.join("profiles", "peaks_r02.json")):
+        try:
+            with open(os.path.join(ROOT, name)) as fh:
+                out.update(json.load(fh))
+        except (OSError, ValueError):
+            pass
     return out
+
+
+def fp64_peak(peaks):
+    """(thread-instructions/s, source)."""
+    if "dfma_Ginstr_s" in peaks:
+        return float(peaks["dfma_Ginstr_s"]) * 1e9, "profiles/peaks_r02.json dfma_Ginstr_s (tools/peaks.cu, measured)"
+    clk = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    return 64 * 148 * clk, "nominal 64 FP64 instr/clk/SM x 148 SMs x max SM clock (no measured probe found)"
 
 
 def run_ours(args):
@@ -334,14 +345,15 @@ def run_ours(args):
     counts = [b - a for a, b in blocks]
 
     numa = sweep_mod.bind_to_gpu_numa(local_rank) if world > 1 else None
-    sw = sweep_mod.Sweep(grid, device=local_rank, dtype=args.dtype, slots=args.slots, what="psf")
+    sw = sweep_mod.Sweep(grid, device=local_rank, dtype=args.dtype, slots=args.slots, what="psf", batch=args.batch)
+    args.slots, args.batch = len(sw.streams), sw.batch
     stack = sw.empty_stack(len(jobs))
     host_ring = False
     try:
         host_stack = sw.empty_stack(len(jobs), host=True)
     except RuntimeError:
         # not enough pinned memory for the whole stack on this host: stream the PSFs through a 64-slot ring
-        host_stack = sw.empty_stack(min(len(jobs), 64), host=True)
+        host_stack = sw.empty_stack(min(len(jobs), 2 * sw.ring_rows), host=True)
         host_ring = True
 
     def barrier():
@@ -407,7 +419,7 @@ def run_ours(args):
     e2e_ee = None
     if args.dtype == "complex128":
         nb = 256
-        ring = stack[: args.slots]
+        ring = stack[: sw.ring_rows]
         ee_dev = torch.empty((len(jobs), nb + 1), dtype=torch.float64, device=stack.device)
         ee_host = torch.empty((len(jobs), nb + 1), dtype=torch.float64, pin_memory=True)
 
@@ -436,35 +448,32 @@ def run_ours(args):
         barrier()
 
     # ---- per-kernel timing for the roofline (separate pass: events around every launch) -------------
+    # The pass kernel is bound by the FP64 pipe (fused passes chain ~5 line FFTs per sweep of the
+    # field, so the HBM model of SURVEY 8d no longer describes it; ncu: ~10 MB of DRAM traffic per launch).  achieved =
+    # FP64 butterfly instructions of the lines really transformed / summed launch durations (CUDA events on the launching
+    # stream, one slot so that launches do not overlap); peak = the measured DFMA issue rate of tools/peaks.cu.
     roofline = None
     passes = {}
     if rank == 0:
-        # one slot, so that launches do not overlap and an event pair brackets exactly one kernel
-        sw1 = sweep_mod.Sweep(grid, device=local_rank, dtype=args.dtype, slots=1, what="psf")
+        sw1 = sweep_mod.Sweep(grid, device=local_rank, dtype=args.dtype, slots=1, what="psf", batch=args.batch)
         sw1.enable_timing(True)
-        sub = jobs[: min(len(jobs), 32)]
+        sub = jobs[: min(len(jobs), 8 * sw1.batch)]
         sw1.run(sub, out=stack[: len(sub)])
         sw1.timing_detail(reset=True)
+        sw1.timing_totals(reset=True)
         s1a = sw1.stats()
         sw1.run(sub, out=stack[: len(sub)])
         det = sw1.timing_detail(reset=True)
+        tot = sw1.timing_totals(reset=True)
         s1b = sw1.stats()
         sw1.enable_timing(False)
         del sw1
         elem = 16 if args.dtype == "complex128" else 8
         half_fft2_bytes = 2 * elem * grid * grid  # one read + one write of the field: half of SURVEY 8(d)'s 64 N^2
-        tot_ms = sum(v[0] for v in det.values())
-        tot_launch = sum(v[1] for v in det.values())
-        alg = sum(k[1] * half_fft2_bytes * v[1] for k, v in det.items())
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-                peaks = json.load(fh)
-        except OSError:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = alg / (tot_ms * 1e-3) / 1e9 if tot_ms else 0.0
-        actual = tot_launch * half_fft2_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms else 0.0
+        tot_ms, tot_launch = tot["ms"], tot["launches"]
+        alg = tot["line_fft_sweeps"] * half_fft2_bytes
+        peaks = load_peaks()
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
@@ -472,18 +481,38 @@ def run_ours(args):
         except (OSError, ValueError):
             pass
         for (col, nfft), (m, c) in sorted(det.items()):
-            passes[f"{'col' if col else 'row'}x{nfft}"] = {"launches": c, "avg_us": 1e3 * m / c,
-                                                            "sweep_GBps": half_fft2_bytes * c / (m * 1e-3) / 1e9}
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": "pass_kernel (all row/column instantiations)",
-                    "avg_launch_us": 1e3 * tot_ms / max(tot_launch, 1),
-                    "algorithmic_bytes_per_launch": alg / max(tot_launch, 1),
-                    "sweep_GBps": actual, "sweep_frac": actual / peak,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                    "fp64": fp64_view(grid, args.dtype, s1a, s1b, tot_ms, peaks),
-                    "note": "achieved counts 32*N^2 B per line-FFT sweep (SURVEY 8d: 64*N^2 per FFT2); a pass chains several "
-                            "line FFTs per sweep and lines blanked by an aperture mask are neither loaded nor transformed, so achieved exceeds "
-                            "the HBM peak; sweep_GBps = upper bound of the real read+write bytes of the field / time"}
+            passes[f"{'col' if col else 'row'}x{nfft}"] = {"launches": c, "avg_us": 1e3 * m / c}
+        lines = int(s1b["lines_transformed"] - s1a["lines_transformed"])
+        sweeps = int(s1b["line_ffts_run"] - s1a["line_ffts_run"])
+        per_line = FP64_INSTR_PER_LINE_FFT.get((grid, args.dtype))
+        peak_i, peak_src = fp64_peak(peaks)
+        hbm_model = {"achieved_GBps": alg / (tot_ms * 1e-3) / 1e9 if tot_ms else None, "peak_GBps": hbm_peak,
+                     "x_hbm_peak": alg / (tot_ms * 1e-3) / 1e9 / hbm_peak if tot_ms else None,
+                     "algorithmic_bytes_per_launch": alg / max(tot_launch, 1),
+                     "note": "SURVEY 8d convention: 32*N^2 B per line-FFT sweep (64*N^2 per FFT2) / launch time.  Not a "
+                             "roofline fraction: fused passes chain several line FFTs per sweep of the field and blanked "
+                             "lines are never touched, so this exceeds the HBM peak by construction"}
+        if per_line and tot_ms:
+            ach = lines * per_line / (tot_ms * 1e-3)
+            wall_ach = (int(st1["lines_transformed"] - st0["lines_transformed"]) * per_line) / (ms * 1e-3)
+            roofline = {"bound": "fp64", "achieved": ach / 1e9, "peak": peak_i / 1e9, "unit": "Ginstr/s", "frac": ach / peak_i,
+                        "traffic": traffic, "kernel": "pass_kernel (row and column instantiations, batched launches)",
+                        "avg_launch_us": 1e3 * tot_ms / max(tot_launch, 1), "launches_timed": tot_launch,
+                        "wavefronts_per_launch": tot["wavefront_passes"] / max(tot_launch, 1),
+                        "fp64_instr_per_line_fft": per_line, "lines_transformed": lines,
+                        "active_line_fraction": lines / max(sweeps * grid, 1),
+                        "peak_source": peak_src,
+                        "wall": {"achieved": wall_ach / 1e9, "frac": wall_ach / peak_i,
+                                 "note": "same count over the whole timed region of `value` (all slots overlapping, every kernel included)"},
+                        "algorithmic_model_x_hbm": hbm_model,
+                        "note": "FP64 butterfly instructions (SASS count, table/mask multiplies excluded) of the lines really "
+                                "transformed / pass-kernel launch time; the kernel keeps its working set in registers and "
+                                "shared memory, DRAM traffic is `traffic` bytes per launch (ncu)"}
+        else:
+            roofline = {"bound": "hbm", "achieved": hbm_model["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                        "frac": hbm_model["x_hbm_peak"], "traffic": traffic, "kernel": "pass_kernel",
+                        "avg_launch_us": 1e3 * tot_ms / max(tot_launch, 1),
+                        "note": hbm_model["note"] + "; no FP64 instruction count is tabulated for this grid / precision"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) + parity of the same wavelengths in the same run -------------
     # (BASELINE.md 4.4 / SURVEY 8d: max|amp_gpu - amp_ref| / max|amp_ref| <= 1e-10 for complex128, 1e-4 for complex64)
@@ -496,7 +525,7 @@ def run_ours(args):
         procs = cpu_procs()
         # the sample: the wavelengths whose chain takes the other propagator route (35 instead of 39 FFT2: different
         # inside/outside decisions of the pilot beam), then wavelengths spread evenly over the sweep, one per core
-        sw1 = sweep_mod.Sweep(grid, device=local_rank, dtype=args.dtype, slots=1, what="amplitude")
+        sw1 = sweep_mod.Sweep(grid, device=local_rank, dtype=args.dtype, slots=1, what="amplitude", batch=1)
         nfft2 = []
         for j in jobs:
             f0 = sw1.stats()["fft2_recorded"]
@@ -549,17 +578,20 @@ def run_ours(args):
             "config": {"workload": f"Ariel_AIRS-CH0.ini {grid}^2 {args.dtype}, {n_wl} wavelengths 1.95-3.9 um per GPU "
                                    f"(rank r = field point r), IMAGE_PLANE |.|^2 only",
                        "grid": grid, "wavelengths_per_gpu": n_wl, "psf_per_step": len(jobs_all), "slots": args.slots,
-                       "l2": f"each wavefront is {16 * grid * grid >> 20} MiB and {args.slots} are in flight (> 126 MB L2 at 2048^2); "
-                             "every PSF is a different wavelength, no flush needed"},
+                       "batch": args.batch,
+                       "l2": f"each wavefront is {(16 if args.dtype == 'complex128' else 8) * grid * grid >> 20} MiB and "
+                             f"{args.slots * args.batch} are in flight (> 126 MB L2 at 2048^2); every PSF is a different "
+                             "wavelength, no flush needed"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h * world,
                     "note": "paos_b200.sweep.Sweep.run over host job dicts; inputs are lens-prescription scalars (kernel "
                             "arguments, no array uploads); every PSF (N*N fp64) is copied to pinned host memory inside the timed region"},
             "gpu_launches": launches * world,
             "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
-            "host_plan_ms_per_psf": 1e3 * t_host / (len(jobs) * args.steps),
+            "wall_ms_per_psf": 1e3 * t_host / (len(jobs) * args.steps),
             "fft2_per_step": int(st1["fft2_recorded"] - st0["fft2_recorded"]) // args.steps * world,
             "pass_launches_per_psf": (st1["pass_launches"] - st0["pass_launches"]) / (len(jobs) * args.steps),
+            "passes_per_psf": (st1["passes_planned"] - st0["passes_planned"]) / (len(jobs) * args.steps),
             "e2e_ee": e2e_ee, "passes": passes, "gather_ms": gather_ms, "gather_first_ms": gather_first_ms,
         }
         emit(line)
@@ -599,7 +631,8 @@ def main():
     ap.add_argument("--dtype", default="complex128", choices=["complex128", "complex64"])
     ap.add_argument("--grid", type=int, default=GRID)
     ap.add_argument("--n-wl", type=int, default=N_WL)
-    ap.add_argument("--slots", type=int, default=4)
+    ap.add_argument("--slots", type=int, default=None, help="host threads / streams (default: 3 batched, 4 unbatched)")
+    ap.add_argument("--batch", type=int, default=None, help="wavefronts per batched launch (default by grid size; 1 = unbatched)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cache-compiled", action="store_true", help="diagnostic: keep the compiled surface records between sweeps")
     args = ap.parse_args()

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PAOS_ABI_VERSION 2
+#define PAOS_ABI_VERSION 3
 #define PAOS_MAX_CHAINED_FFTS 16 /* line FFTs one pass kernel can chain */
 
 enum {
@@ -62,7 +62,7 @@ int paos_abi_version(void);
 const char *paos_last_error(void);
 /* "libpaos_b200 sm_100a source <sha1 of csrc/ + include/ + flags> compiled <date>": which tree this binary was made from */
 const char *paos_build_info(void);
-/* sizeof of a public struct as this library was compiled (0: paos_surface, 1: paos_snapshot, 2: paos_stats; -1 for
+/* sizeof of a public struct as this library was compiled (0: paos_surface, 1: paos_snapshot, 2: paos_stats, 3: paos_chain_args; -1 for
  * anything else): lets a foreign-function binding check its own mirror of the layout */
 long paos_abi_struct_size(int which);
 /* number of usable sm_100 devices (0 when none); never fails */
@@ -215,6 +215,36 @@ int paos_chain_run(paos_wfo *w, double pupil_diameter, double wavelength, double
                    const paos_surface *surfaces, int n_surfaces, paos_snapshot *snapshots, int max_snapshots,
                    int *n_snapshots, paos_snapshot *final_state);
 
+/* ---- batched execution: the `batch` of SURVEY.md section 8(b) --------------------------------------------------
+ * Independent propagations (wavelengths, field points, Monte-Carlo realizations: the joblib fan-out of
+ * paos/core/pipeline.py:140-150) that are at the same point of their chains share their kernel launches: ONE grid runs the
+ * same-axis FFT pass of every wavefront of the batch (a batch index on the grid; each item keeps its own phase tables,
+ * masks, blank-line range and output pointer), one launch builds all their phase tables, one reduces all their stops.
+ * A pass of a single 2048^2 wavefront whose aperture blanks most lines is a wave or two of CTAs and is bound by the latency
+ * of one CTA's chain; the batch fills the machine and amortises the launch.  Results are bit-identical to running the
+ * handles one by one.
+ *
+ * paos_wfo_begin_record: from now on the handle records its device work instead of launching it (host-blocking calls --
+ * paos_wfo_read, paos_wfo_sync, paos_zernike_cov, the *_host_out arguments -- fail with PAOS_ERR_STATE meanwhile).
+ * paos_batch_execute: plans what is still queued on each handle and executes the recorded programs of nb <=
+ * paos_batch_capacity() handles in lockstep on their common stream (same grid size, precision, device and stream
+ * required); the handles leave recording mode.  Asynchronous.  On error every handle of the batch is reset to a
+ * non-recording, empty state.
+ * paos_batch_chain_run: begin_record + paos_chain_run on every handle (args[b]) + paos_batch_execute. */
+typedef struct paos_chain_args {
+    double pupil_diameter, wavelength, zoom, us, ut;
+    const paos_surface *surfaces;
+    int n_surfaces;
+    int max_snapshots;
+    paos_snapshot *snapshots;
+    int *n_snapshots;
+    paos_snapshot *final_state;
+} paos_chain_args;
+int paos_batch_capacity(void);
+int paos_wfo_begin_record(paos_wfo *w);
+int paos_batch_execute(paos_wfo *const *ws, int nb);
+int paos_batch_chain_run(paos_wfo *const *ws, int nb, const paos_chain_args *args);
+
 /* ---- the stand-alone polynomial classes (paos/classes/zernike.py:63-109 `Zernike`, :293-317 `cov`, :388-402 `PolyOrthoNorm`) ----
  * Polynomials at arbitrary points: rho, phi, mask (numpy masked-array convention, may be NULL) are host arrays of npoints
  * entries; points with rho > 1 or mask != 0 give 0.  norm may be NULL (ones).  nterms <= 64.
@@ -239,8 +269,10 @@ int paos_encircled_energy(paos_wfo *w, const void *psf_dev, double dx, double dy
 
 /* ---- statistics -------------------------------------------------------------------------------- */
 typedef struct paos_stats {
-    uint64_t kernel_launches;   /* kernels of this library launched on the handle so far */
+    uint64_t kernel_launches;   /* kernels of this library launched for the handle so far (a batched launch is booked
+                                   once, on the first handle of the batch: the sum over handles is the true count) */
     uint64_t pass_launches;     /* of which FFT line-pass kernels */
+    uint64_t passes_planned;    /* line passes (sweeps of the field) of this wavefront, however they were launched */
     uint64_t fft2_recorded;     /* FFT2s requested through the API (algorithmic count) */
     uint64_t line_ffts_run;     /* 1-D line-FFT batches executed (2 per FFT2) */
     uint64_t lines_transformed; /* single lines actually transformed (a batch is n lines unless an aperture blanks some) */
@@ -252,6 +284,11 @@ int paos_wfo_stats(paos_wfo *w, paos_stats *out);
 int paos_wfo_enable_timing(paos_wfo *w, int enable);
 /* sum of pass-kernel device times (ms) and number of timed launches since the last call */
 int paos_wfo_timing(paos_wfo *w, double *pass_ms, uint64_t *pass_launches);
+/* totals since the last reset: device time of the timed pass launches, their number, the line-FFT sweeps they carried
+ * (chained FFTs summed over the wavefronts of each launch: algorithmic bytes = sweeps * 2 * sizeof(complex) * N^2 in the
+ * convention of SURVEY.md 8d) and the wavefront-passes they served */
+int paos_wfo_timing_totals(paos_wfo *w, double *ms, uint64_t *launches, uint64_t *line_fft_sweeps, uint64_t *wavefronts,
+                           int reset);
 /* the same split by pass kind: col = 0 row pass / 1 column pass, nfft = line FFTs chained in the pass
  * (0..PAOS_MAX_CHAINED_FFTS); reset != 0 clears the bucket after reading it */
 int paos_wfo_timing_detail(paos_wfo *w, int col, int nfft, double *ms, uint64_t *launches, int reset);

@@ -8,14 +8,15 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpaos_b200.so")
+# PAOS_LIB: an experiment variant built by `PAOS_BUILD_TAG=... python paos_b200/build.py` (profiling tools only)
+LIB_PATH = os.environ.get("PAOS_LIB") or os.path.join(HERE, "libpaos_b200.so")
 
 PAOS_OK = 0
 PAOS_ERR_ARG, PAOS_ERR_CUDA, PAOS_ERR_STATE, PAOS_ERR_UNSUPPORTED = -1, -2, -3, -4
 PAOS_C128, PAOS_C64 = 0, 1
 READ_WFO, READ_AMPLITUDE, READ_PHASE, READ_PSF = 0, 1, 2, 3
 SHAPE_ELLIPSE, SHAPE_RECT = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_CHAINED_FFTS = 16
 
 
@@ -31,6 +32,7 @@ class PaosStats(C.Structure):
     _fields_ = [
         ("kernel_launches", C.c_uint64),
         ("pass_launches", C.c_uint64),
+        ("passes_planned", C.c_uint64),
         ("fft2_recorded", C.c_uint64),
         ("line_ffts_run", C.c_uint64),
         ("lines_transformed", C.c_uint64),
@@ -80,6 +82,11 @@ SIGNATURES = {
     "paos_wfo_enable_timing": (_i, [_vp, _i]),
     "paos_wfo_timing": (_i, [_vp, _dp, C.POINTER(C.c_uint64)]),
     "paos_wfo_timing_detail": (_i, [_vp, _i, _i, _dp, C.POINTER(C.c_uint64), _i]),
+    "paos_wfo_timing_totals": (_i, [_vp, _dp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _i]),
+    "paos_batch_capacity": (_i, []),
+    "paos_wfo_begin_record": (_i, [_vp]),
+    "paos_batch_execute": (_i, [C.POINTER(_vp), _i]),
+    "paos_batch_chain_run": (_i, [C.POINTER(_vp), _i, _vp]),
 }
 
 if not os.path.exists(LIB_PATH):

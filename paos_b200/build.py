@@ -10,8 +10,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libpaos_b200.so")
+# PAOS_BUILD_TAG=<tag> builds an experiment variant (with PAOS_NVCC_EXTRA flags) next to the product library:
+# libpaos_b200_<tag>.so, loaded by setting PAOS_LIB to its path (tools/ only; the product and the tests use the default)
+_TAG = os.environ.get("PAOS_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(HERE, "libpaos_b200" + ("_" + _TAG if _TAG else "") + ".so")
 SOURCES = ["runtime.cu", "aux_kernels.cu", "pass_c128.cu", "pass_c64.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -19,7 +22,7 @@ NVCC_FLAGS = [
 ] + (os.environ.get("PAOS_NVCC_EXTRA", "").split())
 
 
-INFO = os.path.join(HERE, "build_info.json")
+INFO = os.path.join(HERE, "build_info" + ("_" + _TAG if _TAG else "") + ".json")
 
 
 def source_hash():
@@ -79,6 +82,13 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    # the roofline probe (tools/peaks.cu): a stand-alone binary, not part of the library
+    probe = os.path.join(HERE, "..", "tools", "peaks.cu")
+    if os.path.exists(probe):
+        r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-o",
+                            os.path.join(HERE, "..", "tools", "peaks_b200"), probe], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for tools/peaks.cu:\n{r.stdout}\n{r.stderr}")
     ver = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout.strip().splitlines()
     with open(INFO, "w") as fh:
         json.dump({"source_hash": want, "nvcc": ver[-1] if ver else "", "flags": NVCC_FLAGS, "sources": SOURCES,

@@ -45,6 +45,16 @@ class Snapshot(C.Structure):
                     propagator=self.propagator.decode())
 
 
+class ChainArgs(C.Structure):
+    """``paos_chain_args`` of ``include/paos_b200.h``: the arguments of ``paos_chain_run`` for one item of a batch."""
+
+    _fields_ = [
+        ("pupil_diameter", C.c_double), ("wavelength", C.c_double), ("zoom", C.c_double), ("us", C.c_double), ("ut", C.c_double),
+        ("surfaces", C.c_void_p), ("n_surfaces", C.c_int), ("max_snapshots", C.c_int), ("snapshots", C.c_void_p),
+        ("n_snapshots", C.c_void_p), ("final_state", C.c_void_p),
+    ]
+
+
 class CompiledChain:
     """``paos_surface`` array of one job plus the host arrays it points to (kept alive here)."""
 
@@ -189,3 +199,28 @@ def run_compiled(wfo, job, cc):
         float(job["field"]["ut"]), cc.array, cc.count, cc.snapshots, len(cc.saved), C.byref(cc.nsnap), C.byref(cc.final)))
     wfo._sync_scalars(cc.final)
     return [cc.snapshots[k].as_dict(cc.n) for k in range(min(cc.nsnap.value, len(cc.saved)))]
+
+
+def run_compiled_batch(wfos, jobs, ccs):
+    """Enqueue the compiled chains of ``jobs`` on ``wfos`` (same stream, grid size and precision) as ONE batch
+    (``paos_batch_chain_run``): the same-axis passes of all items share a kernel launch.  Returns one snapshot list per job."""
+    nb = len(jobs)
+    args = (ChainArgs * nb)()
+    handles = (C.c_void_p * nb)()
+    for b, (wfo, job, cc) in enumerate(zip(wfos, jobs, ccs)):
+        handles[b] = wfo._handle
+        a = args[b]
+        a.pupil_diameter, a.wavelength, a.zoom = float(job["pupil_diameter"]), float(job["wavelength"]), float(job["zoom"])
+        a.us, a.ut = float(job["field"]["us"]), float(job["field"]["ut"])
+        a.surfaces = C.cast(cc.array, C.c_void_p)
+        a.n_surfaces = cc.count
+        a.max_snapshots = len(cc.saved)
+        a.snapshots = C.cast(cc.snapshots, C.c_void_p)
+        a.n_snapshots = C.cast(C.pointer(cc.nsnap), C.c_void_p)
+        a.final_state = C.cast(C.pointer(cc.final), C.c_void_p)
+    _lib.check(_lib.lib.paos_batch_chain_run(handles, nb, C.cast(args, C.c_void_p)))
+    out = []
+    for wfo, cc in zip(wfos, ccs):
+        wfo._sync_scalars(cc.final)
+        out.append([cc.snapshots[k].as_dict(cc.n) for k in range(min(cc.nsnap.value, len(cc.saved)))])
+    return out

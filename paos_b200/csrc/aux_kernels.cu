@@ -103,9 +103,20 @@ struct Norm2Params {
     int ngen;
     GenOp gen[GMAX];
 };
+// the stop reductions of up to BMAX wavefronts in one launch: blockIdx.y = item
+struct Norm2Batch {
+    int nb;
+    int pad;
+    double* partials[BMAX];
+    double* out[BMAX];
+    Norm2Params p[BMAX];
+};
+static_assert(sizeof(Norm2Batch) <= 32764, "Norm2Batch must fit the kernel parameter space");
 
 template <typename R>
-__global__ void __launch_bounds__(256) norm2_partial_kernel(const __grid_constant__ Norm2Params P, double* __restrict__ partials) {
+__global__ void __launch_bounds__(256) norm2_partial_kernel(const __grid_constant__ Norm2Batch B) {
+    const Norm2Params& P = B.p[blockIdx.y];
+    double* __restrict__ partials = B.partials[blockIdx.y];
     const int n = P.n;
     const C<R>* src = reinterpret_cast<const C<R>*>(P.src);
     double acc = 0.0;
@@ -137,7 +148,9 @@ __global__ void __launch_bounds__(256) norm2_partial_kernel(const __grid_constan
     if (threadIdx.x == 0) partials[blockIdx.x] = red[0];
 }
 
-__global__ void norm2_final_kernel(const double* __restrict__ partials, int np, double* __restrict__ out) {
+__global__ void norm2_final_kernel(const __grid_constant__ Norm2Batch B, int np) {
+    const double* __restrict__ partials = B.partials[blockIdx.x];
+    double* __restrict__ out = B.out[blockIdx.x];
     __shared__ double red[256];
     double acc = 0.0;
     for (int i = threadIdx.x; i < np; i += 256) acc += partials[i];
@@ -153,19 +166,34 @@ __global__ void norm2_final_kernel(const double* __restrict__ partials, int np, 
     }
 }
 
+cudaError_t launch_norm2_batch(const Norm2Item* items, int nb, int n, int dtype, int npartials, cudaStream_t st) {
+    if (nb < 1 || nb > BMAX) return cudaErrorInvalidValue;
+    static thread_local Norm2Batch B;
+    B.nb = nb;
+    for (int b = 0; b < nb; ++b) {
+        B.partials[b] = items[b].partials;
+        B.out[b] = items[b].out_slot;
+        B.p[b].src = items[b].src;
+        B.p[b].n = n;
+        B.p[b].ngen = items[b].ngen;
+        for (int i = 0; i < items[b].ngen; ++i) B.p[b].gen[i] = items[b].gen[i];
+    }
+    const dim3 grid((unsigned)npartials, (unsigned)nb);
+    if (dtype == 0) norm2_partial_kernel<double><<<grid, 256, 0, st>>>(B);
+    else norm2_partial_kernel<float><<<grid, 256, 0, st>>>(B);
+    norm2_final_kernel<<<nb, 256, 0, st>>>(B, npartials);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_norm2(const void* src, int n, int dtype, const GenOp* gen, int ngen, double* partials,
                          int npartials, double* out_slot, cudaStream_t st) {
-    Norm2Params P;
-    P.src = src;
-    P.n = n;
-    P.ngen = ngen;
-    for (int i = 0; i < ngen; ++i) {
-        P.gen[i] = gen[i];
-    }
-    if (dtype == 0) norm2_partial_kernel<double><<<npartials, 256, 0, st>>>(P, partials);
-    else norm2_partial_kernel<float><<<npartials, 256, 0, st>>>(P, partials);
-    norm2_final_kernel<<<1, 256, 0, st>>>(partials, npartials, out_slot);
-    return cudaGetLastError();
+    Norm2Item it{};
+    it.src = src;
+    it.ngen = ngen;
+    for (int i = 0; i < ngen; ++i) it.gen[i] = gen[i];
+    it.partials = partials;
+    it.out_slot = out_slot;
+    return launch_norm2_batch(&it, 1, n, dtype, npartials, st);
 }
 
 // ---- virtual zeros made real -----------------------------------------------------------------------------

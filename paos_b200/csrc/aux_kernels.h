@@ -4,6 +4,15 @@
 
 namespace paosb {
 cudaError_t launch_build_tables(const TableBlock& B, cudaStream_t st);
+// one stop reduction (paos/classes/wfo.py:200): sum |src * masks|^2 -> out_slot = (1/sqrt(sum), sum)
+struct Norm2Item {
+    const void* src;  // null: the analytic field of ones
+    int ngen;
+    GenOp gen[GMAX];
+    double* partials;
+    double* out_slot;
+};
+cudaError_t launch_norm2_batch(const Norm2Item* items, int nb, int n, int dtype, int npartials, cudaStream_t st);
 cudaError_t launch_norm2(const void* src, int n, int dtype, const GenOp* gen, int ngen, double* partials,
                          int npartials, double* out_slot, cudaStream_t st);
 cudaError_t launch_zero_outside_band(void* field, int n, int dtype, int axis, int lo, int hi, cudaStream_t st);

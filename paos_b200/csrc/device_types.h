@@ -55,6 +55,20 @@ struct PassParams {
     GenOp gen[GMAX];
 };
 
+// One launch of the pass kernel covers the same-axis passes of up to BMAX independent wavefronts (a batch of wavelengths,
+// fields or Monte-Carlo realizations that are at the same point of their chains): CTA c belongs to item b with
+// start[b] <= c < start[b+1] and works on tile  c - start[b] + p[b].tile_base  of that item's field.  The whole block
+// travels as a __grid_constant__ kernel parameter (up to 32764 bytes on sm_70+).
+// Two capacities are instantiated: CAP = 1 (a single wavefront: 1.7 KB of parameters) and CAP = BMAX.
+constexpr int BMAX = 16;
+template <int CAP> struct BatchParams {
+    int nb;
+    int pad;
+    int start[CAP + 2];
+    PassParams p[CAP];
+};
+static_assert(sizeof(BatchParams<BMAX>) <= 32764, "BatchParams must fit the kernel parameter space");
+
 // one separable phase term: exp(i * c1*c2 * u^2), u = (k - n/2) * d  (QSPACE)  or  (k - n/2) * (1/(n*d))  (QFREQ)
 // TERM_COUNT: real factor count(k)/32, count = sub-pixel centres of pixel k inside a rectangle side (c1 = centre, c2 = full side)
 enum TermKind : int { TERM_QSPACE = 1, TERM_QFREQ = 2, TERM_COUNT = 3 };

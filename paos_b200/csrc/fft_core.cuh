@@ -172,7 +172,8 @@ template <int N_, int E_> struct LineGeom {
 // Forward transform of one line.  v: E registers in strided distribution.  t: thread index inside the
 // line (0..T-1).  sm: this line's exchange buffer.  tw1/tw2: twiddle tables.  SYNC: barrier functor
 // covering all threads of the line.
-template <typename G, typename R, typename SYNC>
+// FIRST_SYNC = false: the caller has already passed a barrier since the last read of the exchange buffer.
+template <typename G, typename R, typename SYNC, bool FIRST_SYNC = true>
 __device__ __forceinline__ void line_fft_fwd(C<R>* v, int t, C<R>* sm, const C<R>* __restrict__ tw1,
                                              const C<R>* __restrict__ tw2, SYNC sync) {
     constexpr int E = G::E, T = G::T, R2 = G::R2, TP = G::TP;
@@ -198,7 +199,7 @@ __device__ __forceinline__ void line_fft_fwd(C<R>* v, int t, C<R>* sm, const C<R
     for (int k1 = 1; k1 < E; ++k1) v[k1] = v[k1] * ldc_ro(tw1 + (k1 - 1) * T + t);
 #endif
 #ifndef PAOS_EXP_NO_SMEM
-    sync();  // previous readers of the buffer are done
+    if constexpr (FIRST_SYNC) sync();  // previous readers of the buffer are done
 #pragma unroll
     for (int k1 = 0; k1 < E; ++k1) stc(sm + k1 * TP + t, v[k1]);
     sync();

@@ -4,6 +4,11 @@
 
 namespace paosb {
 
+#ifdef PAOS_EXP_ROW2  // experiment: two rows per CTA (256 threads, 2 CTAs/SM) like the column kernel
+#define PAOS_ROW_2048 PAOS_CASE(2048, 16, 2, 2, 2, 2)
+#else
+#define PAOS_ROW_2048 PAOS_CASE(2048, 16, 1, 2, 4, 2)
+#endif
 //                 N    E  Wrow Wcol minb(row) minb(col)
 #define PAOS_TILE_TABLE \
     PAOS_CASE(64, 8, 16, 16, 1, 1) \
@@ -11,15 +16,15 @@ namespace paosb {
     PAOS_CASE(256, 16, 4, 4, 2, 2) \
     PAOS_CASE(512, 8, 2, 2, 4, 4) \
     PAOS_CASE(1024, 16, 2, 4, 4, 2) \
-    PAOS_CASE(2048, 16, 1, 2, 4, 2) \
+    PAOS_ROW_2048 \
     PAOS_CASE(4096, 16, 1, 2, 2, 1)
 
 #define PAOS_CASE(N, E, WR, WC, MR, MC)                                                              \
     case N:                                                                                          \
-        return col ? launch_pass_t<double, N, E, WC, true, MC>(P, tw1, tw2, st, device)                 \
-                   : launch_pass_t<double, N, E, WR, false, MR>(P, tw1, tw2, st, device);
+        return col ? launch_pass_t<double, N, E, WC, true, MC>(Ps, nb, tw1, tw2, st, device)                 \
+                   : launch_pass_t<double, N, E, WR, false, MR>(Ps, nb, tw1, tw2, st, device);
 
-cudaError_t launch_pass_c128(int n, bool col, const PassParams& P, const void* tw1, const void* tw2,
+cudaError_t launch_pass_c128(int n, bool col, const PassParams* const* Ps, int nb, const void* tw1, const void* tw2,
                              cudaStream_t st, int device) {
     switch (n) {
         PAOS_TILE_TABLE

@@ -16,10 +16,10 @@ namespace paosb {
 
 #define PAOS_CASE(N, E, WR, WC, MR, MC)                                                              \
     case N:                                                                                          \
-        return col ? launch_pass_t<float, N, E, WC, true, MC>(P, tw1, tw2, st, device)                 \
-                   : launch_pass_t<float, N, E, WR, false, MR>(P, tw1, tw2, st, device);
+        return col ? launch_pass_t<float, N, E, WC, true, MC>(Ps, nb, tw1, tw2, st, device)                 \
+                   : launch_pass_t<float, N, E, WR, false, MR>(Ps, nb, tw1, tw2, st, device);
 
-cudaError_t launch_pass_c64(int n, bool col, const PassParams& P, const void* tw1, const void* tw2,
+cudaError_t launch_pass_c64(int n, bool col, const PassParams* const* Ps, int nb, const void* tw1, const void* tw2,
                              cudaStream_t st, int device) {
     switch (n) {
         PAOS_TILE_TABLE

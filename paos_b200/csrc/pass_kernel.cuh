@@ -32,15 +32,18 @@ __device__ __forceinline__ double disk_rect_q1(double x0, double x1, double y0, 
         const double sL = sqrt(fmax(0.0, 1.0 - L * L));
         const double sU = sqrt(fmax(0.0, 1.0 - U * U));
         // area under the arc = trapezoid under the chord + circular segment
-        const double sn = U * sL - L * sU;  // sin of the angle between the two radius vectors
+        const double sn = U * sL - L * sU;  // sin of the angle th between the two radius vectors
         const double cs = L * U + sL * sU;
-        const double th = atan2(sn, cs);
-        double seg;
-        if (th < 0.05) {
-            const double t2 = th * th;
-            seg = th * t2 * (1.0 / 6.0) * (1.0 - t2 * (1.0 / 20.0) * (1.0 - t2 * (1.0 / 42.0) * (1.0 - t2 * (1.0 / 72.0))));
+        double seg;  // th - sin(th)
+        if (sn < 0.05 && cs > 0.0) {
+            // A pixel subtends a small angle (1/a rad for a semi-axis of a pixels), so this is the branch an edge pixel
+            // takes: th = asin(sn), th - sn = sn^3/6 + 3 sn^5/40 + 15 sn^7/336 + 105 sn^9/3456 + 945 sn^11/42240 + ...
+            // (next term < 1e-14 of the sum at sn = 0.05): no cancellation and no atan2, whose ~150 dependent FP64
+            // instructions on one or two lanes of a warp used to stand on the critical path of the whole line.
+            const double s2 = sn * sn;
+            seg = sn * s2 * (1.0 / 6.0 + s2 * (3.0 / 40.0 + s2 * (15.0 / 336.0 + s2 * (105.0 / 3456.0 + s2 * (945.0 / 42240.0)))));
         } else {
-            seg = th - sn;
+            seg = atan2(sn, cs) - sn;
         }
         area += (0.5 * (sL + sU) - y0) * (U - L) + 0.5 * seg;
     }
@@ -226,16 +229,56 @@ __device__ __forceinline__ void apply_gen(C<R>& v, const GenOp& g, int ix, int i
     v = v * (R)re;
 }
 
+// ---- TMA staging of the along-line phase tables (experiment -DPAOS_TMA_TABLES) ----------------------------------
+// One elected thread asks the bulk-copy engine (cp.async.bulk, 1-D TMA) for the N-entry table of the next position
+// while the current line FFT runs; completion is signalled on an mbarrier in shared memory, and the threads then read
+// their 16 entries with LDS.128 instead of 16 LDG.128 through L1/L2.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, void* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// Where it is used: the column kernels of the 2048^2 and 4096^2 grids, whose two CTAs per SM have the 32-64 KB to spare
+// (measured on AIRS-CH0 2048^2, batches of 8: column passes 2-5 % faster, 521 -> 495 us for the dense final pass).  The row
+// kernel (one line per CTA, four CTAs per SM) would drop to three CTAs per SM and loses what it gains (profiles/README.md).
+// -DPAOS_TMA_TABLES=1 / =0 forces it on / off everywhere for the A/B measurement.
+template <int N, bool COL> __host__ __device__ constexpr bool use_tma_tables() {
+#ifdef PAOS_TMA_TABLES
+    return PAOS_TMA_TABLES != 0;
+#else
+    return COL && N >= 2048;
+#endif
+}
+
 // ---- the pass kernel ---------------------------------------------------------------------------------
 // R: real type; N: line length; E: points per thread; W: lines per CTA; COL: lines are columns.
 // zero store of one tile (and of its read-out); out of line so that it does not share registers with the main path
 template <typename R, int N, int E, int W, bool COL>
-__device__ __noinline__ void store_zero_tile(const PassParams& P) {
+__device__ __noinline__ void store_zero_tile(const PassParams& P, int tile) {
     constexpr int T = N / E;
     const int tid = threadIdx.x;
     const int w = COL ? (tid % W) : (tid / T);
     const int t = COL ? (tid / W) : (tid % T);
-    const int line = ((int)blockIdx.x + P.tile_base) * W + w;
+    const int line = tile * W + w;
     C<R>* dst = reinterpret_cast<C<R>*>(P.dst);
     R* out = reinterpret_cast<R*>(P.dst_real);
     const C<R> zero((R)0, (R)0);
@@ -247,21 +290,38 @@ __device__ __noinline__ void store_zero_tile(const PassParams& P) {
     }
 }
 
-template <typename R, int N, int E, int W, bool COL, int MINB>
+template <typename R, int N, int E, int W, bool COL, int MINB, int CAP>
 __global__ void __launch_bounds__(W*(N / E), MINB)
-    pass_kernel(const __grid_constant__ PassParams P, const C<R>* __restrict__ tw1, const C<R>* __restrict__ tw2) {
+    pass_kernel(const __grid_constant__ BatchParams<CAP> BP, const C<R>* __restrict__ tw1, const C<R>* __restrict__ tw2) {
     using G = LineGeom<N, E>;
     constexpr int T = G::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C<R>* smem = reinterpret_cast<C<R>*>(smem_raw);
 
+    // which wavefront of the batch this CTA works for (CTA-uniform; the parameter block sits in the constant bank)
+    int b = 0;
+    if constexpr (CAP > 1) {
+#pragma unroll 1
+        while (b + 1 < BP.nb && (int)blockIdx.x >= BP.start[b + 1]) ++b;
+    }
+    const PassParams& P = BP.p[b];
+
     const int tid = threadIdx.x;
     const int w = COL ? (tid % W) : (tid / T);
     const int t = COL ? (tid / W) : (tid % T);
-    const int tile = (int)blockIdx.x + P.tile_base;
+    const int tile = (int)blockIdx.x - BP.start[b] + P.tile_base;
     const int line = tile * W + w;
     C<R>* sm = smem + w * G::line_stride(COL ? W : 1, (int)sizeof(C<R>));
     auto sync = [] { __syncthreads(); };
+    constexpr bool kTmaTables = use_tma_tables<N, COL>();
+    // TMA variant: [exchange buffers of the W lines][one table of N entries][mbarrier]
+    C<R>* tabbuf = smem + W * G::line_stride(COL ? W : 1, (int)sizeof(C<R>));
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(tabbuf + N);
+    unsigned tab_phase = 0;
+    if constexpr (kTmaTables) {
+        if (tid == 0) mbar_init(mbar, 1);
+        __syncthreads();
+    }
 
     const C<R>* src = reinterpret_cast<const C<R>*>(P.src);
     C<R>* dst = reinterpret_cast<C<R>*>(P.dst);
@@ -277,10 +337,13 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
     // remembers the band outside which the field is zero ("virtual zeros") and hands it to the next consumer as
     // [in_lo, in_hi] (other axis) or folds it into its tile range (same axis).  Only a fused read-out needs the zeros.
     if (tile < P.tile_lo || tile > P.tile_hi) {
-        if (P.zero_fill | P.readout) store_zero_tile<R, N, E, W, COL>(P);
+        if (P.zero_fill | P.readout) store_zero_tile<R, N, E, W, COL>(P, tile);
         return;
     }
 
+    if constexpr (kTmaTables) {
+        if (tid == 0 && P.tab[0]) bulk_load(tabbuf, P.tab[0], (unsigned)(N * sizeof(C<R>)), mbar);
+    }
     C<R> v[E];
     if (src) {
         // memory outside [in_lo, in_hi] is stale: those elements are zeros that were never written
@@ -303,6 +366,7 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
     }
     for (int pos = 0;; ++pos) {
         // diagonal factors of this position: general (masks, screens, stop scalar), then the along-line table
+#ifndef PAOS_EXP_NO_GEN
         if (P.genmask >> pos & 1) {
             for (int gi = 0; gi < P.ngen; ++gi) {
                 const GenOp& g = P.gen[gi];
@@ -332,10 +396,12 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
                         } else if (r2 >= out6) {
                             if (!obsc) v[j] = C<R>((R)0, (R)0);
                         } else {
+#ifndef PAOS_EXP_NO_EDGE
                             const int idx = t + j * T;
                             double m, fi;
                             gen_factor_slow(g, COL ? line : idx, COL ? idx : line, N, m, fi);
                             v[j] = v[j] * (R)m;
+#endif
                         }
                     }
                 } else if (g.kind == GEN_RECT) {
@@ -369,10 +435,22 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
                 }
             }
         }
+#endif
+#ifdef PAOS_EXP_NO_TAB
+        const C<R>* tab = nullptr;
+#else
         const C<R>* tab = reinterpret_cast<const C<R>*>(P.tab[pos]);
+#endif
         if (tab) {
+            if constexpr (kTmaTables) {
+                mbar_wait(mbar, tab_phase);
+                tab_phase ^= 1u;
 #pragma unroll
-            for (int j = 0; j < E; ++j) v[j] = v[j] * ldc_ro(tab + t + j * T);
+                for (int j = 0; j < E; ++j) v[j] = v[j] * ldc(tabbuf + t + j * T);
+            } else {
+#pragma unroll
+                for (int j = 0; j < E; ++j) v[j] = v[j] * ldc_ro(tab + t + j * T);
+            }
         } else {
             // real scale, with the (-1)^index sign of an fftshift when flagged (index parity = t parity: T is even)
             R s = (R)P.scl[pos];
@@ -388,7 +466,13 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
         if (P.dir[pos] < 0) {
 #pragma unroll
             for (int j = 0; j < E; ++j) v[j] = C<R>(v[j].y, v[j].x);
-            {
+            if constexpr (kTmaTables) {
+                // every thread has consumed the staged table (and the previous exchange): the buffer is free for the
+                // table of the next position, fetched by the copy engine while this transform runs
+                __syncthreads();
+                if (tid == 0 && P.tab[pos + 1]) bulk_load(tabbuf, P.tab[pos + 1], (unsigned)(N * sizeof(C<R>)), mbar);
+                line_fft_fwd<G, R, decltype(sync), false>(v, t, sm, tw1, tw2, sync);
+            } else {
                 // pull the next position's phase table into L1 while this transform runs (one 128-byte line per
                 // prefetch; the table is N complex values, shared by every line of the pass)
                 const char* nxt = reinterpret_cast<const char*>(P.tab[pos + 1]);
@@ -397,12 +481,18 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
 #pragma unroll
                     for (int i = t; i < LINES; i += T) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + (size_t)i * 128));
                 }
+                line_fft_fwd<G, R>(v, t, sm, tw1, tw2, sync);
             }
-            line_fft_fwd<G, R>(v, t, sm, tw1, tw2, sync);
 #pragma unroll
             for (int j = 0; j < E; ++j) v[j] = C<R>(v[j].y, v[j].x);
         } else {
-            {
+            if constexpr (kTmaTables) {
+                // every thread has consumed the staged table (and the previous exchange): the buffer is free for the
+                // table of the next position, fetched by the copy engine while this transform runs
+                __syncthreads();
+                if (tid == 0 && P.tab[pos + 1]) bulk_load(tabbuf, P.tab[pos + 1], (unsigned)(N * sizeof(C<R>)), mbar);
+                line_fft_fwd<G, R, decltype(sync), false>(v, t, sm, tw1, tw2, sync);
+            } else {
                 // pull the next position's phase table into L1 while this transform runs (one 128-byte line per
                 // prefetch; the table is N complex values, shared by every line of the pass)
                 const char* nxt = reinterpret_cast<const char*>(P.tab[pos + 1]);
@@ -411,8 +501,8 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
 #pragma unroll
                     for (int i = t; i < LINES; i += T) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + (size_t)i * 128));
                 }
+                line_fft_fwd<G, R>(v, t, sm, tw1, tw2, sync);
             }
-            line_fft_fwd<G, R>(v, t, sm, tw1, tw2, sync);
         }
     }
     if (P.ctab_out) {
@@ -446,30 +536,43 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
 }
 
 // host-side launcher table -------------------------------------------------------------------------
-template <typename R, int N, int E, int W, bool COL, int MINB>
-cudaError_t launch_pass_t(const PassParams& P0, const void* tw1, const void* tw2, cudaStream_t st, int device) {
+// One launch for the same-axis passes of nb <= BMAX wavefronts (nb = 1: the plain single-wavefront pass).
+template <typename R, int N, int E, int W, bool COL, int MINB, int CAP>
+cudaError_t launch_pass_cap(const PassParams* const* Ps, int nb, const void* tw1, const void* tw2, cudaStream_t st, int device) {
     using G = LineGeom<N, E>;
     constexpr int threads = W * G::T;
-    const size_t smem = (size_t)W * G::line_stride(COL ? W : 1, (int)sizeof(C<R>)) * sizeof(C<R>);
-    auto kern = pass_kernel<R, N, E, W, COL, MINB>;
+    const size_t smem = (size_t)W * G::line_stride(COL ? W : 1, (int)sizeof(C<R>)) * sizeof(C<R>) +
+                        (use_tma_tables<N, COL>() ? (size_t)N * sizeof(C<R>) + 16 : 0);
+    auto kern = pass_kernel<R, N, E, W, COL, MINB, CAP>;
     static bool configured[64] = {};  // per instantiation and device
     if (!configured[device & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured[device & 63] = true;
     }
-    // blank tiles have nothing to do unless they must store zeros (fused read-out, diagnostic zero fill): launch the rest
-    PassParams P = P0;
-    int tiles = N / W;
-    P.tile_base = 0;
-    if (!P.zero_fill && !P.readout) {
-        P.tile_base = P.tile_lo > 0 ? P.tile_lo : 0;
-        tiles = (P.tile_hi < N / W - 1 ? P.tile_hi : N / W - 1) - P.tile_base + 1;
-        if (tiles <= 0) return cudaSuccess;  // the whole field is (virtually) zero after this pass
+    static thread_local BatchParams<CAP> BP;
+    int total = 0, used = 0;
+    for (int i = 0; i < nb; ++i) {
+        // blank tiles have nothing to do unless they must store zeros (fused read-out, diagnostic zero fill): launch the rest
+        PassParams& P = BP.p[used];
+        P = *Ps[i];
+        int tiles = N / W;
+        P.tile_base = 0;
+        if (!P.zero_fill && !P.readout) {
+            P.tile_base = P.tile_lo > 0 ? P.tile_lo : 0;
+            tiles = (P.tile_hi < N / W - 1 ? P.tile_hi : N / W - 1) - P.tile_base + 1;
+            if (tiles <= 0) continue;  // the whole field is (virtually) zero after this pass
+        }
+        BP.start[used] = total;
+        total += tiles;
+        ++used;
     }
+    if (used == 0) return cudaSuccess;
+    BP.nb = used;
+    BP.start[used] = total;
     static const bool pdl = getenv("PAOS_NO_PDL") == nullptr;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)tiles);
+    cfg.gridDim = dim3((unsigned)total);
     cfg.blockDim = dim3((unsigned)threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -478,7 +581,15 @@ cudaError_t launch_pass_t(const PassParams& P0, const void* tw1, const void* tw2
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, P, reinterpret_cast<const C<R>*>(tw1), reinterpret_cast<const C<R>*>(tw2));
+    return cudaLaunchKernelEx(&cfg, kern, BP, reinterpret_cast<const C<R>*>(tw1), reinterpret_cast<const C<R>*>(tw2));
+}
+
+// One launch for the same-axis passes of nb <= BMAX wavefronts (nb = 1: the plain single-wavefront pass).
+template <typename R, int N, int E, int W, bool COL, int MINB>
+cudaError_t launch_pass_t(const PassParams* const* Ps, int nb, const void* tw1, const void* tw2, cudaStream_t st, int device) {
+    if (nb < 1 || nb > BMAX) return cudaErrorInvalidValue;
+    if (nb == 1) return launch_pass_cap<R, N, E, W, COL, MINB, 1>(Ps, nb, tw1, tw2, st, device);
+    return launch_pass_cap<R, N, E, W, COL, MINB, BMAX>(Ps, nb, tw1, tw2, st, device);
 }
 
 }  // namespace paosb

@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -162,8 +163,24 @@ struct ZeroBand {
 
 struct TimedLaunch {
     cudaEvent_t a, b;
-    int nfft;
+    int nfft;   // line FFTs chained, summed over the wavefronts of a batched launch
     int col;
+    int items;  // wavefronts served by the launch
+};
+
+// Deferred execution.  While a handle is *recording*, every device launch the library would make for it is appended to
+// its program instead; paos_batch_execute then walks the programs of up to BMAX handles in lockstep on one stream and
+// issues ONE launch for the heads that are of the same kind (the same-axis passes of several wavelengths, their table
+// builds, their stop reductions).  Inside one handle the order of the records is the order of the stream, so everything
+// that relies on stream order (table pool reuse per flush, screen recycling, stop scalars) holds unchanged.
+enum RecKind { REC_TABLES = 1, REC_PASS = 2, REC_NORM2 = 3, REC_FN = 4 };
+struct Rec {
+    int kind = 0;
+    bool col = false;
+    PassParams P;                         // REC_PASS
+    std::vector<TableSpec> specs;         // REC_TABLES
+    Norm2Item norm;                       // REC_NORM2
+    std::function<int(cudaStream_t)> fn;  // REC_FN: anything else (screens, uploads, zero fill), run per handle
 };
 
 struct paos_wfo {
@@ -192,12 +209,18 @@ struct paos_wfo {
     static constexpr int NSLOTS = 256;
     static constexpr int NPARTIALS = 148 * 8;
 
+    bool recording = false;
+    std::vector<Rec> program;
+    std::vector<void*> retired_pools;  // table pools outgrown while recording: still referenced by the program
+
     paos_stats stats{};
     bool timing = false;
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
     double timed_ms[2][KMAX + 1] = {};
     uint64_t timed_n[2][KMAX + 1] = {};
+    double timed_total_ms = 0.0;       // since the last paos_wfo_timing_totals(reset)
+    uint64_t timed_total_launches = 0, timed_total_sweeps = 0, timed_total_items = 0;
 };
 
 static int set_device(paos_wfo* w) {
@@ -486,34 +509,166 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
     return PAOS_OK;
 }
 
-static int launch_pass(paos_wfo* w, bool col, const PassParams& P) {
+static void account_pass(paos_wfo* w, bool col, const PassParams& P) {
+    w->stats.passes_planned++;
+    w->stats.line_ffts_run += (uint64_t)P.nfft;
+    const int W = tile_width(w->n, w->dtype, col), tiles = w->n / W;
+    const int active = std::max(0, std::min(P.tile_hi, tiles - 1) - std::max(P.tile_lo, 0) + 1);
+    w->stats.lines_transformed += (uint64_t)P.nfft * (uint64_t)active * (uint64_t)W;
+}
+
+// one launch of the pass kernel for the same-axis passes Ps[0..nb) of handles that share grid size, precision, device and
+// stream; launch counts and timing are booked on `lead`
+static int launch_pass_group(paos_wfo* lead, bool col, const PassParams* const* Ps, int nb, cudaStream_t st) {
     cudaEvent_t ea = nullptr, eb = nullptr;
-    if (w->timing) {
+    if (lead->timing) {
         for (cudaEvent_t* e : {&ea, &eb}) {
-            if (!w->event_pool.empty()) {
-                *e = w->event_pool.back();
-                w->event_pool.pop_back();
+            if (!lead->event_pool.empty()) {
+                *e = lead->event_pool.back();
+                lead->event_pool.pop_back();
             } else {
                 CU(cudaEventCreate(e));
             }
         }
-        CU(cudaEventRecord(ea, w->stream));
+        CU(cudaEventRecord(ea, st));
     }
-    cudaError_t e = (w->dtype == PAOS_C128) ? launch_pass_c128(w->n, col, P, w->tw.tw1, w->tw.tw2, w->stream, w->device)
-                                            : launch_pass_c64(w->n, col, P, w->tw.tw1, w->tw.tw2, w->stream, w->device);
+    cudaError_t e = (lead->dtype == PAOS_C128) ? launch_pass_c128(lead->n, col, Ps, nb, lead->tw.tw1, lead->tw.tw2, st, lead->device)
+                                               : launch_pass_c64(lead->n, col, Ps, nb, lead->tw.tw1, lead->tw.tw2, st, lead->device);
     if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "pass kernel launch failed: %s", cudaGetErrorString(e));
-    if (w->timing) {
-        CU(cudaEventRecord(eb, w->stream));
-        w->timed.push_back(TimedLaunch{ea, eb, P.nfft, col ? 1 : 0});
+    if (lead->timing) {
+        CU(cudaEventRecord(eb, st));
+        int nfft = 0;
+        for (int i = 0; i < nb; ++i) nfft += Ps[i]->nfft;
+        lead->timed.push_back(TimedLaunch{ea, eb, nfft, col ? 1 : 0, nb});
     }
-    w->stats.kernel_launches++;
-    w->stats.pass_launches++;
-    w->stats.line_ffts_run += (uint64_t)P.nfft;
-    {
-        const int W = tile_width(w->n, w->dtype, col), tiles = w->n / W;
-        const int active = std::max(0, std::min(P.tile_hi, tiles - 1) - std::max(P.tile_lo, 0) + 1);
-        w->stats.lines_transformed += (uint64_t)P.nfft * (uint64_t)active * (uint64_t)W;
+    lead->stats.kernel_launches++;
+    lead->stats.pass_launches++;
+    return PAOS_OK;
+}
+
+static int launch_tables(paos_wfo* lead, const std::vector<TableSpec>& specs, cudaStream_t st) {
+    for (size_t s = 0; s < specs.size(); s += TB_MAX) {
+        TableBlock B{};
+        B.n = lead->n;
+        B.dtype = lead->dtype;
+        B.ntab = (int)std::min<size_t>(TB_MAX, specs.size() - s);
+        for (int i = 0; i < B.ntab; ++i) B.spec[i] = specs[s + i];
+        cudaError_t e = launch_build_tables(B, st);
+        if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "table builder launch failed: %s", cudaGetErrorString(e));
+        lead->stats.kernel_launches++;
     }
+    return PAOS_OK;
+}
+
+static int launch_norm2_group(paos_wfo* lead, const Norm2Item* items, int nb, cudaStream_t st) {
+    cudaError_t e = launch_norm2_batch(items, nb, lead->n, lead->dtype, paos_wfo::NPARTIALS, st);
+    if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "stop reduction launch failed: %s", cudaGetErrorString(e));
+    lead->stats.kernel_launches += 2;
+    return PAOS_OK;
+}
+
+// record (deferred mode) or execute right away
+static int do_pass(paos_wfo* w, bool col, const PassParams& P) {
+    account_pass(w, col, P);
+    if (w->recording) {
+        w->program.emplace_back();
+        Rec& r = w->program.back();
+        r.kind = REC_PASS;
+        r.col = col;
+        r.P = P;
+        return PAOS_OK;
+    }
+    const PassParams* one = &P;
+    return launch_pass_group(w, col, &one, 1, w->stream);
+}
+
+static int do_tables(paos_wfo* w, std::vector<TableSpec>& specs) {
+    if (specs.empty()) return PAOS_OK;
+    if (w->recording) {
+        w->program.emplace_back();
+        Rec& r = w->program.back();
+        r.kind = REC_TABLES;
+        r.specs = specs;
+        return PAOS_OK;
+    }
+    return launch_tables(w, specs, w->stream);
+}
+
+static int do_norm2(paos_wfo* w, const Norm2Item& item) {
+    if (w->recording) {
+        w->program.emplace_back();
+        Rec& r = w->program.back();
+        r.kind = REC_NORM2;
+        r.norm = item;
+        return PAOS_OK;
+    }
+    return launch_norm2_group(w, &item, 1, w->stream);
+}
+
+// anything else that touches the device: fn(stream) returns a PAOS_* status; launches counts kernels for the statistics
+static int do_fn(paos_wfo* w, int launches, std::function<int(cudaStream_t)> fn) {
+    w->stats.kernel_launches += (uint64_t)launches;
+    if (w->recording) {
+        w->program.emplace_back();
+        Rec& r = w->program.back();
+        r.kind = REC_FN;
+        r.fn = std::move(fn);
+        return PAOS_OK;
+    }
+    return fn(w->stream);
+}
+
+// Execute the recorded programs of nb handles in lockstep (see Rec).  All handles share n, dtype, device and stream.
+static int execute_programs(paos_wfo** ws, int nb) {
+    paos_wfo* lead = ws[0];
+    cudaStream_t st = lead->stream;
+    std::vector<size_t> at((size_t)nb, 0);
+    std::vector<TableSpec> specs;
+    std::vector<Norm2Item> norms;
+    const PassParams* group[BMAX];
+    for (;;) {
+        int n_fn = 0, n_tab = 0, n_norm = 0, n_row = 0, n_col = 0, live = 0;
+        for (int b = 0; b < nb; ++b) {
+            if (at[b] >= ws[b]->program.size()) continue;
+            ++live;
+            const Rec& r = ws[b]->program[at[b]];
+            if (r.kind == REC_FN) ++n_fn;
+            else if (r.kind == REC_TABLES) ++n_tab;
+            else if (r.kind == REC_NORM2) ++n_norm;
+            else if (r.col) ++n_col;
+            else ++n_row;
+        }
+        if (!live) break;
+        int rc = PAOS_OK;
+        if (n_fn) {
+            for (int b = 0; b < nb; ++b)
+                while (at[b] < ws[b]->program.size() && ws[b]->program[at[b]].kind == REC_FN) {
+                    if ((rc = ws[b]->program[at[b]].fn(st))) return rc;
+                    ++at[b];
+                }
+        } else if (n_tab) {
+            specs.clear();
+            for (int b = 0; b < nb; ++b)
+                if (at[b] < ws[b]->program.size() && ws[b]->program[at[b]].kind == REC_TABLES) {
+                    const Rec& r = ws[b]->program[at[b]++];
+                    specs.insert(specs.end(), r.specs.begin(), r.specs.end());
+                }
+            if ((rc = launch_tables(lead, specs, st))) return rc;
+        } else if (n_norm) {
+            norms.clear();
+            for (int b = 0; b < nb; ++b)
+                if (at[b] < ws[b]->program.size() && ws[b]->program[at[b]].kind == REC_NORM2) norms.push_back(ws[b]->program[at[b]++].norm);
+            if ((rc = launch_norm2_group(lead, norms.data(), (int)norms.size(), st))) return rc;
+        } else {
+            const bool col = n_col > n_row;
+            int k = 0;
+            for (int b = 0; b < nb; ++b)
+                if (at[b] < ws[b]->program.size() && ws[b]->program[at[b]].kind == REC_PASS && ws[b]->program[at[b]].col == col)
+                    group[k++] = &ws[b]->program[at[b]++].P;
+            if ((rc = launch_pass_group(lead, col, group, k, st))) return rc;
+        }
+    }
+    for (int b = 0; b < nb; ++b) ws[b]->program.clear();
     return PAOS_OK;
 }
 
@@ -522,8 +677,12 @@ static int ensure_pool(paos_wfo* w, size_t need_tables) {
     const size_t need = need_tables * per;
     if (need <= w->tab_cap) return PAOS_OK;
     if (w->tab_pool) {
-        CU(cudaStreamSynchronize(w->stream));
-        CU(cudaFree(w->tab_pool));
+        if (w->recording) {
+            w->retired_pools.push_back(w->tab_pool);  // recorded passes still point into it
+        } else {
+            CU(cudaStreamSynchronize(w->stream));
+            CU(cudaFree(w->tab_pool));
+        }
         w->tab_pool = nullptr;
     }
     size_t cap = need * 2;
@@ -534,19 +693,10 @@ static int ensure_pool(paos_wfo* w, size_t need_tables) {
 
 static int run_plan(paos_wfo* w, Plan& plan) {
     // tables first (one or more launches of the builder), then the passes
-    for (size_t s = 0; s < plan.specs.size(); s += TB_MAX) {
-        TableBlock B{};
-        B.n = w->n;
-        B.dtype = w->dtype;
-        B.ntab = (int)std::min<size_t>(TB_MAX, plan.specs.size() - s);
-        for (int i = 0; i < B.ntab; ++i) B.spec[i] = plan.specs[s + i];
-        cudaError_t e = launch_build_tables(B, w->stream);
-        if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "table builder launch failed: %s", cudaGetErrorString(e));
-        w->stats.kernel_launches++;
-    }
+    int rc = do_tables(w, plan.specs);
+    if (rc) return rc;
     for (PlannedPass& pp : plan.passes) {
-        int rc = launch_pass(w, pp.col, pp.P);
-        if (rc) return rc;
+        if ((rc = do_pass(w, pp.col, pp.P))) return rc;
     }
     return PAOS_OK;
 }
@@ -582,11 +732,12 @@ static int flush_ops(paos_wfo* w, std::vector<Op>& ops, int readout, void* dst_r
 // write the virtual zeros of `field` (see ZeroBand) before something other than a pass kernel reads it
 static int materialize_band(paos_wfo* w, void* field, ZeroBand& band) {
     if (!band.valid) return PAOS_OK;
-    cudaError_t e = launch_zero_outside_band(field, w->n, w->dtype, band.axis, band.lo, band.hi, w->stream);
-    if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "zero fill launch failed: %s", cudaGetErrorString(e));
-    w->stats.kernel_launches++;
+    const int n = w->n, dtype = w->dtype, axis = band.axis, lo = band.lo, hi = band.hi;
     band.valid = false;
-    return PAOS_OK;
+    return do_fn(w, 1, [=](cudaStream_t st) {
+        cudaError_t e = launch_zero_outside_band(field, n, dtype, axis, lo, hi, st);
+        return e == cudaSuccess ? PAOS_OK : fail(PAOS_ERR_CUDA, "zero fill launch failed: %s", cudaGetErrorString(e));
+    });
 }
 
 static int flush_all(paos_wfo* w, int readout = 0, void* dst_real = nullptr, bool discard = false) {
@@ -600,8 +751,13 @@ static int resolve_timing(paos_wfo* w) {
     for (TimedLaunch& t : w->timed) {
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, t.a, t.b));
-        w->timed_ms[t.col][t.nfft] += ms;
-        w->timed_n[t.col][t.nfft] += 1;
+        const int bucket = std::min(KMAX, (t.nfft + t.items / 2) / std::max(t.items, 1));  // average chain length of the launch
+        w->timed_ms[t.col][bucket] += ms;
+        w->timed_n[t.col][bucket] += 1;
+        w->timed_total_ms += ms;
+        w->timed_total_launches += 1;
+        w->timed_total_sweeps += (uint64_t)t.nfft;
+        w->timed_total_items += (uint64_t)t.items;
         w->event_pool.push_back(t.a);
         w->event_pool.push_back(t.b);
     }
@@ -636,6 +792,7 @@ long paos_abi_struct_size(int which) {
         case 0: return (long)sizeof(paos_surface);
         case 1: return (long)sizeof(paos_snapshot);
         case 2: return (long)sizeof(paos_stats);
+        case 3: return (long)sizeof(paos_chain_args);
         default: return -1;
     }
 }
@@ -716,6 +873,7 @@ int paos_wfo_destroy(paos_wfo* w) {
     for (double* p : w->screens_busy) cudaFree(p);
     if (w->scratch_field) cudaFree(w->scratch_field);
     if (w->tab_pool) cudaFree(w->tab_pool);
+    for (void* p : w->retired_pools) cudaFree(p);
     if (w->partials) cudaFree(w->partials);
     if (w->slots) cudaFree(w->slots);
     if (w->own_field && w->field) cudaFree(w->field);
@@ -752,14 +910,83 @@ int paos_wfo_materialize(paos_wfo* w) {
 
 int paos_wfo_sync(paos_wfo* w) {
     if (!w) return fail(PAOS_ERR_ARG, "null handle");
+    if (w->recording) return fail(PAOS_ERR_STATE, "the handle is recording: run paos_batch_execute first");
     int rc = flush_all(w);
     if (rc) return rc;
     CU(cudaStreamSynchronize(w->stream));
+    for (void* p : w->retired_pools) cudaFree(p);
+    w->retired_pools.clear();
     return resolve_timing(w);
 }
 
+// ---- deferred execution of several handles as one batch -----------------------------------------------
+int paos_wfo_begin_record(paos_wfo* w) {
+    if (!w) return fail(PAOS_ERR_ARG, "null handle");
+    if (w->recording) return fail(PAOS_ERR_STATE, "the handle is recording already");
+    w->recording = true;
+    w->program.clear();
+    return PAOS_OK;
+}
+
+static void abandon_records(paos_wfo* const* ws, int nb) {
+    for (int b = 0; b < nb; ++b)
+        if (ws[b]) {
+            ws[b]->recording = false;
+            ws[b]->program.clear();
+            ws[b]->ops.clear();
+        }
+}
+
+int paos_batch_execute(paos_wfo* const* ws, int nb) {
+    if (!ws || nb < 1) return fail(PAOS_ERR_ARG, "no handles");
+    if (nb > BMAX) return fail(PAOS_ERR_ARG, "a batch holds at most %d wavefronts", BMAX);
+    for (int b = 0; b < nb; ++b) {
+        if (!ws[b]) return fail(PAOS_ERR_ARG, "null handle in the batch");
+        if (ws[b]->n != ws[0]->n || ws[b]->dtype != ws[0]->dtype || ws[b]->device != ws[0]->device || ws[b]->stream != ws[0]->stream) {
+            abandon_records(ws, nb);
+            return fail(PAOS_ERR_ARG, "the handles of a batch must share grid size, precision, device and stream");
+        }
+        for (int c = 0; c < b; ++c)
+            if (ws[c] == ws[b]) {
+                abandon_records(ws, nb);
+                return fail(PAOS_ERR_ARG, "a handle appears twice in the batch");
+            }
+    }
+    int rc = set_device(ws[0]);
+    std::vector<paos_wfo*> hs(ws, ws + nb);
+    for (int b = 0; b < nb && !rc; ++b) {
+        // what is still queued behind the last flush (nothing after a final read-out) is planned now, still deferred
+        if (hs[b]->recording && !hs[b]->dropped) rc = flush_all(hs[b]);
+    }
+    for (int b = 0; b < nb; ++b) hs[b]->recording = false;
+    if (!rc) rc = execute_programs(hs.data(), nb);
+    if (rc) abandon_records(ws, nb);
+    return rc;
+}
+
+int paos_batch_chain_run(paos_wfo* const* ws, int nb, const paos_chain_args* args) {
+    if (!ws || !args || nb < 1) return fail(PAOS_ERR_ARG, "null argument");
+    if (nb > BMAX) return fail(PAOS_ERR_ARG, "a batch holds at most %d wavefronts", BMAX);
+    for (int b = 0; b < nb; ++b) {
+        int rc = ws[b] ? paos_wfo_begin_record(ws[b]) : fail(PAOS_ERR_ARG, "null handle in the batch");
+        if (!rc) {
+            const paos_chain_args& a = args[b];
+            rc = paos_chain_run(ws[b], a.pupil_diameter, a.wavelength, a.zoom, a.us, a.ut, a.surfaces, a.n_surfaces, a.snapshots,
+                                a.max_snapshots, a.n_snapshots, a.final_state);
+        }
+        if (rc) {
+            abandon_records(ws, nb);
+            return rc;
+        }
+    }
+    return paos_batch_execute(ws, nb);
+}
+
+int paos_batch_capacity(void) { return BMAX; }
+
 int paos_wfo_upload(paos_wfo* w, const void* host_src) {
     if (!w || !host_src) return fail(PAOS_ERR_ARG, "null argument");
+    if (w->recording) return fail(PAOS_ERR_STATE, "the handle is recording");
     int rc = set_device(w);
     if (rc) return rc;
     w->ops.clear();
@@ -788,6 +1015,7 @@ int paos_wfo_upload_device(paos_wfo* w, const void* dev_src) {
 
 static int read_impl(paos_wfo* w, int what, void* dst, bool to_host, bool discard = false) {
     if (!w || !dst) return fail(PAOS_ERR_ARG, "null argument");
+    if (w->recording && to_host) return fail(PAOS_ERR_STATE, "a recording handle cannot be read to the host: execute the batch first");
     if (what < PAOS_READ_WFO || what > PAOS_READ_PSF) return fail(PAOS_ERR_ARG, "unknown read-out %d", what);
     if (w->dropped) return fail(PAOS_ERR_STATE, "the field was discarded by a final read-out: reset the handle before re-using it");
     int rc = set_device(w);
@@ -798,7 +1026,15 @@ static int read_impl(paos_wfo* w, int what, void* dst, bool to_host, bool discar
         if (rc) return rc;
         rc = materialize_band(w, w->field, w->band);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(dst, w->field, nn * w->elem, to_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, w->stream));
+        {
+            const void* src = w->field;
+            const size_t bytes = nn * w->elem;
+            rc = do_fn(w, 0, [=](cudaStream_t st) {
+                cudaError_t e = cudaMemcpyAsync(dst, src, bytes, to_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st);
+                return e == cudaSuccess ? PAOS_OK : fail(PAOS_ERR_CUDA, "field copy failed: %s", cudaGetErrorString(e));
+            });
+            if (rc) return rc;
+        }
     } else {
         const size_t rbytes = nn * (w->elem / 2);
         void* dev_out = dst;
@@ -814,9 +1050,13 @@ static int read_impl(paos_wfo* w, int what, void* dst, bool to_host, bool discar
         } else {
             rc = materialize_band(w, w->field, w->band);
             if (rc) return rc;
-            cudaError_t e = launch_readout(w->field, w->n, w->dtype, what, dev_out, w->stream);
-            if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "read-out launch failed: %s", cudaGetErrorString(e));
-            w->stats.kernel_launches++;
+            const void* src = w->field;
+            const int n = w->n, dtype = w->dtype;
+            rc = do_fn(w, 1, [=](cudaStream_t st) {
+                cudaError_t e = launch_readout(src, n, dtype, what, dev_out, st);
+                return e == cudaSuccess ? PAOS_OK : fail(PAOS_ERR_CUDA, "read-out launch failed: %s", cudaGetErrorString(e));
+            });
+            if (rc) return rc;
         }
         if (to_host) {
             CU(cudaMemcpyAsync(dst, dev_out, rbytes, cudaMemcpyDeviceToHost, w->stream));
@@ -906,21 +1146,16 @@ int paos_wfo_aperture(paos_wfo* w, int shape, double ixc, double iyc, double ihx
         double* buf;
         rc = get_screen(w, &buf);
         if (rc) return rc;
-        TableBlock B{};
-        B.n = w->n;
-        B.dtype = w->dtype;
-        B.ntab = 2;
-        B.spec[0].out = buf;
-        B.spec[0].kind = TABLE_COUNT;
-        B.spec[0].cnt_c = ixc;
-        B.spec[0].cnt_full = ihx;
-        B.spec[1].out = buf + w->n;
-        B.spec[1].kind = TABLE_COUNT;
-        B.spec[1].cnt_c = iyc;
-        B.spec[1].cnt_full = ihy;
-        cudaError_t e = launch_build_tables(B, w->stream);
-        if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "table builder launch failed: %s", cudaGetErrorString(e));
-        w->stats.kernel_launches++;
+        std::vector<TableSpec> specs(2);
+        specs[0].out = buf;
+        specs[0].kind = TABLE_COUNT;
+        specs[0].cnt_c = ixc;
+        specs[0].cnt_full = ihx;
+        specs[1].out = buf + w->n;
+        specs[1].kind = TABLE_COUNT;
+        specs[1].cnt_c = iyc;
+        specs[1].cnt_full = ihy;
+        if ((rc = do_tables(w, specs))) return rc;
         g.kind = GEN_RECT;
         g.ptr0 = buf;
         g.ptr1 = buf + w->n;
@@ -961,10 +1196,13 @@ int paos_wfo_make_stop(paos_wfo* w) {
     w->ops = tail;
     if (w->materialized && (rc = materialize_band(w, w->field, w->band))) return rc;
     double* slot = w->slots + 2 * (w->slot_next++ % paos_wfo::NSLOTS);
-    cudaError_t e = launch_norm2(w->materialized ? w->field : nullptr, w->n, w->dtype, gens.data(), (int)gens.size(), w->partials,
-                                 paos_wfo::NPARTIALS, slot, w->stream);
-    if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "stop reduction launch failed: %s", cudaGetErrorString(e));
-    w->stats.kernel_launches += 2;
+    Norm2Item item{};
+    item.src = w->materialized ? w->field : nullptr;
+    item.ngen = (int)gens.size();
+    for (int i = 0; i < item.ngen; ++i) item.gen[i] = gens[i];
+    item.partials = w->partials;
+    item.out_slot = slot;
+    if ((rc = do_norm2(w, item))) return rc;
     GenOp g{};
     g.kind = GEN_SCALE_DEV;
     g.ptr0 = slot;
@@ -1002,7 +1240,12 @@ int paos_wfo_phase_screen(paos_wfo* w, const double* host_screen, double wl) {
     double* buf;
     rc = get_screen(w, &buf);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(buf, host_screen, (size_t)w->n * w->n * sizeof(double), cudaMemcpyHostToDevice, w->stream));
+    const size_t bytes = (size_t)w->n * w->n * sizeof(double);
+    rc = do_fn(w, 0, [=](cudaStream_t st) {
+        cudaError_t e = cudaMemcpyAsync(buf, host_screen, bytes, cudaMemcpyHostToDevice, st);
+        return e == cudaSuccess ? PAOS_OK : fail(PAOS_ERR_CUDA, "screen upload failed: %s", cudaGetErrorString(e));
+    });
+    if (rc) return rc;
     return paos_wfo_phase_screen_device(w, buf, wl);
 }
 
@@ -1044,7 +1287,12 @@ static int upload_mask(paos_wfo* w, const unsigned char* host_mask, unsigned cha
     double* buf;
     int rc = get_screen(w, &buf);  // n*n doubles are more than enough for n*n bytes
     if (rc) return rc;
-    CU(cudaMemcpyAsync(buf, host_mask, (size_t)w->n * w->n, cudaMemcpyHostToDevice, w->stream));
+    const size_t bytes = (size_t)w->n * w->n;
+    rc = do_fn(w, 0, [=](cudaStream_t st) {
+        cudaError_t e = cudaMemcpyAsync(buf, host_mask, bytes, cudaMemcpyHostToDevice, st);
+        return e == cudaSuccess ? PAOS_OK : fail(PAOS_ERR_CUDA, "mask upload failed: %s", cudaGetErrorString(e));
+    });
+    if (rc) return rc;
     *dev = reinterpret_cast<unsigned char*>(buf);
     return PAOS_OK;
 }
@@ -1055,6 +1303,7 @@ int paos_wfo_zernike_masked(paos_wfo* w, int nterms, const int* m, const int* n,
     if (nterms < 1) return fail(PAOS_ERR_ARG, "need at least one Zernike term");
     if (origin != 0 && origin != 1) return fail(PAOS_ERR_ARG, "origin must be 0 ('x') or 1 ('y')");
     if (!(radius > 0.0)) return fail(PAOS_ERR_ARG, "radius must be positive");
+    if (w->recording && wfe_host_out) return fail(PAOS_ERR_STATE, "a recording handle cannot return the screen to the host");
     int rc = set_device(w);
     if (rc) return rc;
     double* screen;
@@ -1065,9 +1314,11 @@ int paos_wfo_zernike_masked(paos_wfo* w, int nterms, const int* m, const int* n,
     for (int s = 0; s < nterms; s += ZERN_MAX) {
         ZernParams Z;
         if ((rc = fill_zern(w->n, Z, s, nterms, m, n, coef, nullptr, radius, dx, dy, offset, origin))) return rc;
-        cudaError_t e = launch_zernike(Z, dmask, screen, w->stream);
-        if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "zernike launch failed: %s", cudaGetErrorString(e));
-        w->stats.kernel_launches++;
+        rc = do_fn(w, 1, [=](cudaStream_t st) {
+            cudaError_t e = launch_zernike(Z, dmask, screen, st);
+            return e == cudaSuccess ? PAOS_OK : fail(PAOS_ERR_CUDA, "zernike launch failed: %s", cudaGetErrorString(e));
+        });
+        if (rc) return rc;
     }
     if (wfe_host_out) {
         CU(cudaMemcpyAsync(wfe_host_out, screen, (size_t)w->n * w->n * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
@@ -1087,6 +1338,7 @@ int paos_zernike_cov(paos_wfo* w, int nterms, const int* m, const int* n, const 
     if (nterms < 1 || nterms > ZERN_MAX) return fail(PAOS_ERR_ARG, "covariance supports 1..%d polynomials", ZERN_MAX);
     if (origin != 0 && origin != 1) return fail(PAOS_ERR_ARG, "origin must be 0 ('x') or 1 ('y')");
     if (!(radius > 0.0)) return fail(PAOS_ERR_ARG, "radius must be positive");
+    if (w->recording) return fail(PAOS_ERR_STATE, "paos_zernike_cov is synchronous: not available on a recording handle");
     int rc = set_device(w);
     if (rc) return rc;
     ZernParams Z;
@@ -1139,22 +1391,26 @@ int paos_wfo_psd(paos_wfo* w, double A, double B, double C, double fknee, double
     if ((noise1 == nullptr) != (noise2 == nullptr)) return fail(PAOS_ERR_ARG, "pass both noise arrays or neither");
     int rc = set_device(w);
     if (rc) return rc;
+    if (w->recording && wfe_host_out) return fail(PAOS_ERR_STATE, "a recording handle cannot return the screen to the host");
     const size_t nn = (size_t)w->n * w->n;
+    const int n = w->n, dtype = w->dtype;
     double *d1, *d2, *screen;
     if ((rc = get_screen(w, &d1)) || (rc = get_screen(w, &d2)) || (rc = get_screen(w, &screen))) return rc;
-    if (noise1) {
-        CU(cudaMemcpyAsync(d1, noise1, nn * sizeof(double), cudaMemcpyHostToDevice, w->stream));
-        CU(cudaMemcpyAsync(d2, noise2, nn * sizeof(double), cudaMemcpyHostToDevice, w->stream));
-    } else {
-        cudaError_t e = launch_normal(seed, 1u, w->n, d1, w->stream);
-        if (e == cudaSuccess) e = launch_normal(seed, 2u, w->n, d2, w->stream);
-        if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "noise launch failed: %s", cudaGetErrorString(e));
-        w->stats.kernel_launches += 2;
-    }
     if (!w->scratch_field) CU(cudaMalloc(&w->scratch_field, nn * w->elem));
-    cudaError_t e = launch_real_to_complex(d1, w->n, w->dtype, w->scratch_field, w->stream);
-    if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "launch failed: %s", cudaGetErrorString(e));
-    w->stats.kernel_launches++;
+    void* scratch = w->scratch_field;
+    rc = do_fn(w, noise1 ? 1 : 3, [=](cudaStream_t st) {
+        cudaError_t e;
+        if (noise1) {
+            e = cudaMemcpyAsync(d1, noise1, nn * sizeof(double), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d2, noise2, nn * sizeof(double), cudaMemcpyHostToDevice, st);
+        } else {
+            e = launch_normal(seed, 1u, n, d1, st);
+            if (e == cudaSuccess) e = launch_normal(seed, 2u, n, d2, st);
+        }
+        if (e == cudaSuccess) e = launch_real_to_complex(d1, n, dtype, scratch, st);
+        return e == cudaSuccess ? PAOS_OK : fail(PAOS_ERR_CUDA, "PSD noise stage failed: %s", cudaGetErrorString(e));
+    });
+    if (rc) return rc;
     // F = fft2(noise) * filter ; wfe = real(ifft2(F)) (numpy default normalisation: 1/(N*N) on the inverse)
     std::vector<Op> ops;
     Op f{};
@@ -1179,9 +1435,11 @@ int paos_wfo_psd(paos_wfo* w, double A, double B, double C, double fknee, double
     ops.push_back(f);
     rc = run_on_scratch(w, ops);
     if (rc) return rc;
-    e = launch_psd_finalize(w->scratch_field, w->n, w->dtype, d2, SR, unit_scale, screen, w->stream);
-    if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "launch failed: %s", cudaGetErrorString(e));
-    w->stats.kernel_launches++;
+    rc = do_fn(w, 1, [=](cudaStream_t st) {
+        cudaError_t e = launch_psd_finalize(scratch, n, dtype, d2, SR, unit_scale, screen, st);
+        return e == cudaSuccess ? PAOS_OK : fail(PAOS_ERR_CUDA, "launch failed: %s", cudaGetErrorString(e));
+    });
+    if (rc) return rc;
     w->stats.fft2_recorded += 2;
     if (wfe_host_out) {
         CU(cudaMemcpyAsync(wfe_host_out, screen, nn * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
@@ -1335,11 +1593,12 @@ int paos_encircled_energy(paos_wfo* w, const void* psf_dev, double dx, double dy
         CU(cudaMemsetAsync(w->ee_hist, 0, (4096 + 2) * sizeof(double), w->stream));
     }
     const double inv_bin = (double)nbins / (r_unit * r_max);
-    cudaError_t e = launch_encircled_energy(psf_dev, w->n, w->dtype == PAOS_C128 ? 0 : 1, dx, dy, xc, yc, inv_bin, nbins, w->ee_hist,
-                                            ee_dev_out, w->stream);
-    if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "encircled-energy launch failed: %s", cudaGetErrorString(e));
-    w->stats.kernel_launches += 2;
-    return PAOS_OK;
+    double* hist = w->ee_hist;
+    const int n = w->n, is_float = w->dtype == PAOS_C128 ? 0 : 1;
+    return do_fn(w, 2, [=](cudaStream_t st) {
+        cudaError_t e = launch_encircled_energy(psf_dev, n, is_float, dx, dy, xc, yc, inv_bin, nbins, hist, ee_dev_out, st);
+        return e == cudaSuccess ? PAOS_OK : fail(PAOS_ERR_CUDA, "encircled-energy launch failed: %s", cudaGetErrorString(e));
+    });
 }
 
 int paos_wfo_stats(paos_wfo* w, paos_stats* out) {
@@ -1365,6 +1624,19 @@ int paos_wfo_timing(paos_wfo* w, double* pass_ms, uint64_t* pass_launches) {
         }
     if (pass_ms) *pass_ms = ms;
     if (pass_launches) *pass_launches = n;
+    return PAOS_OK;
+}
+
+int paos_wfo_timing_totals(paos_wfo* w, double* ms, uint64_t* launches, uint64_t* line_fft_sweeps, uint64_t* wavefronts, int reset) {
+    if (!w) return fail(PAOS_ERR_ARG, "null handle");
+    if (ms) *ms = w->timed_total_ms;
+    if (launches) *launches = w->timed_total_launches;
+    if (line_fft_sweeps) *line_fft_sweeps = w->timed_total_sweeps;
+    if (wavefronts) *wavefronts = w->timed_total_items;
+    if (reset) {
+        w->timed_total_ms = 0.0;
+        w->timed_total_launches = w->timed_total_sweeps = w->timed_total_items = 0;
+    }
     return PAOS_OK;
 }
 

@@ -70,21 +70,36 @@ def bind_to_gpu_numa(device):
         return None
 
 
-class Sweep:
-    """Persistent executor for jobs of one grid size on one GPU."""
+def default_batch(gridsize):
+    """Wavefronts per batched launch.  A pass of one 2048^2 wavefront whose aperture blanks most lines is 270-820 CTAs, a
+    wave or two of the 592 lines a B200 holds: several wavefronts per grid fill the machine and amortise the launch.
+    Smaller grids need more items for the same effect; 4096^2 passes are already many waves."""
+    n = int(gridsize)
+    return 4 if n >= 4096 else 8 if n >= 2048 else 16
 
-    def __init__(self, gridsize, device=0, dtype="complex128", slots=None, what="psf"):
+
+class Sweep:
+    """Persistent executor for jobs of one grid size on one GPU.
+
+    ``slots`` host threads / CUDA streams, each owning ``batch`` wavefronts: a slot takes ``batch`` consecutive jobs, plans
+    their chains (``paos_batch_chain_run``) and the library runs them in lockstep, one kernel launch per pass for the whole
+    batch.  ``batch=1`` is the unbatched executor (one wavefront per slot)."""
+
+    def __init__(self, gridsize, device=0, dtype="complex128", slots=None, what="psf", batch=None):
         import torch
 
         if what not in READS:
             raise ValueError(f"what must be one of {sorted(READS)}")
         self.n = int(gridsize)
+        cap = int(_lib.lib.paos_batch_capacity())
+        if batch is None:
+            batch = default_batch(self.n)
+        self.batch = max(1, min(int(batch), cap))
         if slots is None:
-            # 2048^2 and up: a pass fills the machine, extra slots only overlap the tails and the device-to-host copies
-            # (measured at 2048^2: device-resident throughput equal from 2 to 6 slots, end to end +4 % from 3 to 4);
-            # smaller grids are launch-bound and gain from more host threads / streams (512^2 AIRS 9.8 k -> 13.9 k
-            # PSF/s from 3 to 6 slots)
-            slots = 4 if self.n >= 2048 else 6
+            # batched: two slots are enough to overlap one batch's host planning and device-to-host copies with the
+            # other's kernels (a third one covers the tails); unbatched (batch=1): see the round-1 measurements --
+            # 2048^2 gains nothing beyond 4 slots, launch-bound small grids gain up to 6
+            slots = 3 if self.batch > 1 else (4 if self.n >= 2048 else 6)
         self.device = int(device)
         self.dtype = dtype
         self.what = what
@@ -92,9 +107,17 @@ class Sweep:
         self.tdev = torch.device("cuda", self.device)
         self.rdtype = torch.float64 if dtype == "complex128" else torch.float32
         self.streams = [torch.cuda.Stream(device=self.tdev) for _ in range(slots)]
-        self.wfos = [WFO(1.0, 1.0e-6, self.n, 1.0, device=self.device, dtype=dtype, stream=s) for s in self.streams]
+        # wfos[s][i]: wavefront i of slot s; all wavefronts of a slot share the slot's stream
+        self.slot_wfos = [[WFO(1.0, 1.0e-6, self.n, 1.0, device=self.device, dtype=dtype, stream=s) for _ in range(self.batch)]
+                          for s in self.streams]
+        self.wfos = [w for ws in self.slot_wfos for w in ws]
         self._pool = None
         self._screens = {}  # device copies of grid-sag maps shared between jobs
+
+    @property
+    def ring_rows(self):
+        """Rows a result ring must hold a multiple of (every wavefront in flight owns one row)."""
+        return len(self.streams) * self.batch
 
     def empty_stack(self, count, host=False):
         torch = self.torch
@@ -108,13 +131,15 @@ class Sweep:
 
         ``ee``: ``dict(r_max=..., nbins=...)`` also reduces every PSF (``what="psf"``) to its encircled-energy curve on the
         device (``paos_b200/ee.py``) into ``ee_out[k]`` (``[len(jobs), nbins + 1]`` float64, allocated when None) and,
-        if given, the pinned ``ee_host_out``; ``out`` may then be a ring of a multiple of ``slots`` wavefronts, so that a
-        sweep moves kilobytes per PSF instead of ``8 N^2`` bytes.  The curves are returned as ``meta[k]["ee"]`` views.
+        if given, the pinned ``ee_host_out``; ``out`` may then be a ring of a multiple of ``ring_rows`` wavefronts, so that
+        a sweep moves kilobytes per PSF instead of ``8 N^2`` bytes.  The curves are returned as ``meta[k]["ee"]`` views.
 
         ``out``: device stack (allocated when None).  ``host_out``: optional pinned host stack that also receives
         every result (asynchronous device-to-host copies inside the pipeline; a stack shorter than ``jobs`` is used
-        as a ring).  ``native``: run each chain through ``paos_chain_run`` (C++ per-surface loop) instead of the
-        Python driver; ``cache_compiled=False`` rebuilds the native surface records of every job on every call.
+        as a ring of a multiple of ``ring_rows`` rows -- a row is valid once ``run`` has returned or been overwritten,
+        which only suits a consumer that reads after the sweep).  ``native``: run each chain through ``paos_chain_run`` /
+        ``paos_batch_chain_run`` (C++ per-surface loop) instead of the Python driver; ``cache_compiled=False`` rebuilds
+        the native surface records of every job on every call.
         Returns ``(out, meta)`` with one ``meta`` dict of host scalars per job, after all device work has completed.
         """
         import ctypes as C
@@ -123,13 +148,14 @@ class Sweep:
         if out is None:
             out = self.empty_stack(len(jobs))
         code = READS[self.what]
-        nslots = len(self.wfos)
-        if out.shape[0] < len(jobs) and (ee is None or out.shape[0] % nslots):
-            raise ValueError("out is shorter than jobs: only an encircled-energy sweep may use it as a ring, of a multiple of `slots` rows")
-        if host_out is not None and host_out.shape[0] < len(jobs) and host_out.shape[0] % nslots:
-            # rows are written by slot k % nslots: a ring whose length is not a multiple of `slots` would let two slot
-            # streams copy into the same pinned row with no ordering between them
-            raise ValueError("host_out is shorter than jobs: as a ring it must hold a multiple of `slots` rows")
+        nslots, B = len(self.streams), self.batch
+        if out.shape[0] < len(jobs) and (ee is None or out.shape[0] % self.ring_rows):
+            raise ValueError("out is shorter than jobs: only an encircled-energy sweep may use it as a ring, of a multiple of "
+                             "`ring_rows` (= slots * batch) rows")
+        if host_out is not None and host_out.shape[0] < len(jobs) and host_out.shape[0] % self.ring_rows:
+            # rows are written by the wavefront that owns job k: a ring whose length is not a multiple of the wavefronts
+            # in flight would let two streams copy into the same pinned row with no ordering between them
+            raise ValueError("host_out is shorter than jobs: as a ring it must hold a multiple of `ring_rows` rows")
         if ee is not None:
             if self.what != "psf":
                 raise ValueError("encircled energy needs what='psf'")
@@ -141,43 +167,40 @@ class Sweep:
 
         meta = [None] * len(jobs)
 
-        def do_job(k, job):
-            s = k % nslots
-            wfo, stream = self.wfos[s], self.streams[s]
-            dst = out[k % out.shape[0]]
-            use_native = native
-            if use_native:
-                # whole chain planned and enqueued inside the library (paos_chain_run)
-                if not cache_compiled:
-                    job.pop("_compiled", None)
-                try:
-                    cc = chain_mod.compile_job(job, psd_noise(job) if psd_noise is not None else None, device=self.device,
-                                               screen_cache=self._screens)
-                except NotImplementedError:
-                    use_native = False  # e.g. orthonormal Zernikes, resampled grid sag: the Python driver handles them
-            if use_native:
-                if not cc.saved:
-                    raise ValueError(f"job {job.get('tag', k)} saves no surface")
-                for idx in cc.saved:
-                    cc.set_readout(idx, -1, None)
-                # the sweep keeps nothing but this read-out: the last pass need not store the complex field
-                cc.set_readout(cc.saved[-1], code, dst.data_ptr(), final=True)
-                try:
-                    last = chain_mod.run_compiled(wfo, job, cc)[-1]
-                except NotImplementedError:
-                    # the chain met a surface the native runner cannot take as compiled (a grid-sag map behind a change of
-                    # sampling: its screen was resampled for the INIT pitch); the Python driver restarts the job from INIT
-                    use_native = False
-            if not use_native:
-                def snapshot(w, item):
-                    _lib.check(_lib.lib.paos_wfo_read_device(w._handle, code, C.c_void_p(dst.data_ptr())))
-                    return dict(wz=w.wz, distancetofocus=w.distancetofocus, fratio=w.fratio, dx=w.dx, dy=w.dy, wl=w.wl,
-                                extent=w.extent, propagator=w.propagator)
+        def compile_native(k, job):
+            """Compiled chain of job k with its read-out wired to out[k], or None when the native runner cannot take it."""
+            if not native:
+                return None
+            if not cache_compiled:
+                job.pop("_compiled", None)
+            try:
+                cc = chain_mod.compile_job(job, psd_noise(job) if psd_noise is not None else None, device=self.device,
+                                           screen_cache=self._screens)
+            except NotImplementedError:
+                return None  # e.g. orthonormal Zernikes, resampled grid sag: the Python driver handles them
+            if not cc.saved:
+                raise ValueError(f"job {job.get('tag', k)} saves no surface")
+            for idx in cc.saved:
+                cc.set_readout(idx, -1, None)
+            # the sweep keeps nothing but this read-out: the last pass need not store the complex field
+            cc.set_readout(cc.saved[-1], code, out[k % out.shape[0]].data_ptr(), final=True)
+            return cc
 
-                res = run(job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"],
-                          job["opt_chain"], wfo=wfo, snapshot=snapshot, psd_noise=psd_noise(job) if psd_noise is not None else None)
-                last = res[max(res.keys())] if res else {}
-                last = {k2: v for k2, v in last.items() if k2 not in ("aperture", "wfe")}
+        def python_driver(k, job, wfo):
+            dst = out[k % out.shape[0]]
+
+            def snapshot(w, item):
+                _lib.check(_lib.lib.paos_wfo_read_device(w._handle, code, C.c_void_p(dst.data_ptr())))
+                return dict(wz=w.wz, distancetofocus=w.distancetofocus, fratio=w.fratio, dx=w.dx, dy=w.dy, wl=w.wl,
+                            extent=w.extent, propagator=w.propagator)
+
+            res = run(job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"],
+                      job["opt_chain"], wfo=wfo, snapshot=snapshot, psd_noise=psd_noise(job) if psd_noise is not None else None)
+            last = res[max(res.keys())] if res else {}
+            return {k2: v for k2, v in last.items() if k2 not in ("aperture", "wfe")}
+
+        def finish(k, job, wfo, stream, last):
+            dst = out[k % out.shape[0]]
             last["tag"] = job.get("tag", str(k))
             meta[k] = last
             if ee is not None:
@@ -191,15 +214,42 @@ class Sweep:
                 with torch.cuda.stream(stream):
                     host_out[k % host_out.shape[0]].copy_(dst, non_blocking=True)
 
+        def do_group(s, ks):
+            """Jobs ``ks`` (at most ``batch`` of them) on slot s."""
+            wfos, stream = self.slot_wfos[s], self.streams[s]
+            ccs = [compile_native(k, jobs[k]) for k in ks]
+            nat = [i for i, cc in enumerate(ccs) if cc is not None]
+            lasts = [None] * len(ks)
+            if nat:
+                try:
+                    if len(nat) == 1:
+                        i = nat[0]
+                        lasts[i] = chain_mod.run_compiled(wfos[i], jobs[ks[i]], ccs[i])[-1]
+                    else:
+                        res = chain_mod.run_compiled_batch([wfos[i] for i in nat], [jobs[ks[i]] for i in nat], [ccs[i] for i in nat])
+                        for i, r in zip(nat, res):
+                            lasts[i] = r[-1]
+                except NotImplementedError:
+                    # a chain met a surface the native runner cannot take as compiled (a grid-sag map behind a change of
+                    # sampling: its screen was resampled for the INIT pitch); the Python driver restarts these jobs from INIT
+                    for i in nat:
+                        lasts[i] = None
+            for i, k in enumerate(ks):
+                if lasts[i] is None:
+                    lasts[i] = python_driver(k, jobs[k], wfos[i])
+                finish(k, jobs[k], wfos[i], stream, lasts[i])
+
+        groups = [list(range(g, min(g + B, len(jobs)))) for g in range(0, len(jobs), B)]
+
         def do_slot(s):
             # one host thread per slot: the C++ planner and the launches run without the GIL (ctypes releases it),
-            # so the slots' host work overlaps; jobs of a slot stay in order on the slot's stream
+            # so the slots' host work overlaps; the groups of a slot stay in order on the slot's stream
             torch.cuda.set_device(self.device)
-            for k in range(s, len(jobs), nslots):
-                do_job(k, jobs[k])
+            for g in range(s, len(groups), nslots):
+                do_group(s, groups[g])
 
         distinct = len({id(j) for j in jobs}) == len(jobs)  # a job dict caches per-call native state
-        if threads and distinct and nslots > 1 and len(jobs) >= 2 * nslots:
+        if threads and distinct and nslots > 1 and len(groups) >= 2 * nslots:
             if self._pool is None:
                 from concurrent.futures import ThreadPoolExecutor
 
@@ -207,8 +257,8 @@ class Sweep:
             for f in [self._pool.submit(do_slot, s) for s in range(nslots)]:
                 f.result()
         else:
-            for k, job in enumerate(jobs):
-                do_job(k, job)
+            for g, ks in enumerate(groups):
+                do_group(g % nslots, ks)
         for stream in self.streams:
             stream.synchronize()
         return out, meta
@@ -225,7 +275,7 @@ class Sweep:
             _lib.check(_lib.lib.paos_wfo_enable_timing(w._handle, 1 if on else 0))
 
     def timing_detail(self, reset=True):
-        """{(col, nfft): (ms, launches)} summed over the slots."""
+        """{(col, nfft): (ms, launches)} summed over the wavefronts (nfft: average chain length of a batched launch)."""
         import ctypes as C
 
         out = {}
@@ -239,6 +289,21 @@ class Sweep:
                         a = out.get((col, nfft), (0.0, 0))
                         out[(col, nfft)] = (a[0] + ms.value, a[1] + cnt.value)
         return out
+
+    def timing_totals(self, reset=True):
+        """Device time of the timed pass launches, their number, the line-FFT sweeps and the wavefront-passes they carried."""
+        import ctypes as C
+
+        tot = dict(ms=0.0, launches=0, line_fft_sweeps=0, wavefront_passes=0)
+        for w in self.wfos:
+            _lib.check(_lib.lib.paos_wfo_sync(w._handle))
+            ms, a, b, c = C.c_double(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+            _lib.check(_lib.lib.paos_wfo_timing_totals(w._handle, C.byref(ms), C.byref(a), C.byref(b), C.byref(c), 1 if reset else 0))
+            tot["ms"] += ms.value
+            tot["launches"] += a.value
+            tot["line_fft_sweeps"] += b.value
+            tot["wavefront_passes"] += c.value
+        return tot
 
 
 def gather_stack(local, counts, dst=0, group=None):

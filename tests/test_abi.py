@@ -83,4 +83,31 @@ def test_ctypes_mirrors_have_the_compiled_layout():
     assert _lib.lib.paos_abi_struct_size(0) == C.sizeof(chain.Surface)
     assert _lib.lib.paos_abi_struct_size(1) == C.sizeof(chain.Snapshot)
     assert _lib.lib.paos_abi_struct_size(2) == C.sizeof(_lib.PaosStats)
+    assert _lib.lib.paos_abi_struct_size(3) == C.sizeof(chain.ChainArgs)
     assert _lib.lib.paos_abi_struct_size(99) == -1
+
+
+def test_build_record_matches_the_tree():
+    """The loaded library says which source tree it was compiled from (paos_build_info); it must be this one."""
+    import importlib.util
+
+    from paos_b200 import _lib
+
+    spec = importlib.util.spec_from_file_location("_paos_b200_build", os.path.join(ROOT, "paos_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    info = _lib.lib.paos_build_info().decode()
+    assert mod.source_hash() in info, f"stale library: {info}"
+
+
+def test_batch_entry_points_validate_their_arguments():
+    from paos_b200 import _lib
+
+    assert 2 <= _lib.lib.paos_batch_capacity() <= 64
+    assert _lib.lib.paos_wfo_begin_record(None) == _lib.PAOS_ERR_ARG
+    assert _lib.lib.paos_batch_execute(None, 1) == _lib.PAOS_ERR_ARG
+    hs = (C.c_void_p * 2)()
+    assert _lib.lib.paos_batch_execute(hs, 0) == _lib.PAOS_ERR_ARG
+    assert _lib.lib.paos_batch_execute(hs, 2) == _lib.PAOS_ERR_ARG  # null handles
+    assert _lib.lib.paos_batch_chain_run(hs, 2, None) == _lib.PAOS_ERR_ARG
+    assert _lib.lib.paos_batch_execute(hs, _lib.lib.paos_batch_capacity() + 1) == _lib.PAOS_ERR_ARG

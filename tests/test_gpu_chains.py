@@ -216,13 +216,21 @@ def test_sweep_host_ring_and_python_fallback():
     z1 = [it for it in jobs[2]["opt_chain"].values() if it["type"] == "Zernike"][0]
     z1["Zorthonorm"] = True
     z1["aperture"] = dict(shape="elliptical", type="aperture", xrad=0.009, yrad=0.008, xc=np.nan, yc=np.nan)
-    sw = Sweep(256, slots=2, what="amplitude")
+    sw = Sweep(256, slots=2, what="amplitude", batch=1)
     ring = sw.empty_stack(2, host=True)
     out, meta = sw.run(jobs, host_out=ring)
     out = out.cpu().numpy()
     assert len(meta) == 5 and all(m is not None for m in meta)
     # slot k % 2 of the ring holds the last job written to it: jobs 4 and 3
     assert np.array_equal(ring[0].numpy(), out[4]) and np.array_equal(ring[1].numpy(), out[3])
+    with pytest.raises(ValueError):
+        sw.run(jobs, host_out=sw.empty_stack(3, host=True))  # a ring must hold a multiple of slots * batch rows
+    # the same jobs in batches of four wavefronts: the refused job leaves its batch and runs through the Python driver
+    swb = Sweep(256, slots=1, what="amplitude", batch=4)
+    full = swb.empty_stack(5, host=True)
+    outb, metab = swb.run(jobs, host_out=full)
+    assert np.array_equal(outb.cpu().numpy(), out) and np.array_equal(full.numpy(), out)
+    assert [m["tag"] for m in metab] == [m["tag"] for m in meta]
     for k in (1, 2):
         job = jobs[k]
         ref = paos_b200.run(job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"], job["opt_chain"])

@@ -51,9 +51,10 @@ def test_sweep_gathers_curves_instead_of_psfs():
     from oracle import paos_np
 
     jobs = configs.airs_ch0(grid=256, n_wl=6)
-    sw = Sweep(256, slots=2, what="psf")
+    sw = Sweep(256, slots=1, what="psf", batch=2)
     full, meta_full = sw.run(jobs)
-    ring = sw.empty_stack(2)  # two wavefront-sized buffers for six jobs
+    assert sw.ring_rows == 2
+    ring = sw.empty_stack(sw.ring_rows)  # two wavefront-sized buffers for six jobs
     import torch
 
     host = torch.empty((len(jobs), 65), dtype=torch.float64, pin_memory=True)

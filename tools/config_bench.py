@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--dtype", default="complex128")
     ap.add_argument("--slots", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=None, help="wavefronts per batched launch (default by grid size; 1 = unbatched)")
     args = ap.parse_args()
     import torch
 
@@ -44,7 +45,7 @@ def main():
             continue
         jobs, mode = make()
         n = jobs[0]["gridsize"]
-        sw = Sweep(n, slots=args.slots, what="psf", dtype=args.dtype)
+        sw = Sweep(n, slots=args.slots, what="psf", dtype=args.dtype, batch=args.batch)
         stack = sw.empty_stack(len(jobs))
         sw.run(jobs, out=stack)  # warm-up (also compiles the native surface records of every job: parse-time work)
         st0 = sw.stats()
@@ -54,9 +55,11 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         st1 = sw.stats()
-        rec = {"grid": n, "jobs": len(jobs), "psf_per_s": len(jobs) / dt, "ms_per_psf": 1e3 * dt / len(jobs),
+        rec = {"grid": n, "jobs": len(jobs), "batch": sw.batch, "slots": len(sw.streams), "psf_per_s": len(jobs) / dt,
+               "ms_per_psf": 1e3 * dt / len(jobs),
                "fft2_per_psf": (st1["fft2_recorded"] - st0["fft2_recorded"]) / len(jobs),
-               "passes_per_psf": (st1["pass_launches"] - st0["pass_launches"]) / len(jobs),
+               "passes_per_psf": (st1["passes_planned"] - st0["passes_planned"]) / len(jobs),
+               "pass_launches_per_psf": (st1["pass_launches"] - st0["pass_launches"]) / len(jobs),
                "launches_per_psf": (st1["kernel_launches"] - st0["kernel_launches"]) / len(jobs)}
         rec["algorithmic_GBps"] = rec["fft2_per_psf"] * 64 * n * n * rec["psf_per_s"] / 1e9 * (1 if args.dtype == "complex128" else 0.5)
         if args.cpu:
