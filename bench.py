@@ -274,17 +274,24 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
-def timed_steps(torch, sweep, jobs, stack, host_stack, steps):
-    """Device time (ms) of `steps` sweeps: events on the current stream fenced against every slot stream."""
+def timed_steps(torch, sweep, jobs, stack, host_stack, steps, extra_streams=(), before=None, after=None, **run_kw):
+    """Device time (ms) of `steps` sweeps: events on the current stream fenced against every slot stream (and
+    `extra_streams`: the gather's side stream); `before()` / `after()` bracket every sweep inside the timed region."""
     cur = torch.cuda.current_stream()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     start.record(cur)
     for s in sweep.streams:
         s.wait_event(start)
+    for s in extra_streams:
+        s.wait_event(start)
     for _ in range(steps):
-        sweep.run(jobs, out=stack, host_out=host_stack, cache_compiled=CACHE_COMPILED)
-    for s in sweep.streams:
+        if before is not None:
+            before()
+        sweep.run(jobs, out=stack, host_out=host_stack, cache_compiled=CACHE_COMPILED, **run_kw)
+        if after is not None:
+            after()
+    for s in list(sweep.streams) + list(extra_streams):
         e = torch.cuda.Event()
         e.record(s)
         cur.wait_event(e)
@@ -347,7 +354,9 @@ def run_ours(args):
     numa = sweep_mod.bind_to_gpu_numa(local_rank) if world > 1 else None
     sw = sweep_mod.Sweep(grid, device=local_rank, dtype=args.dtype, slots=args.slots, what="psf", batch=args.batch)
     args.slots, args.batch = len(sw.streams), sw.batch
-    stack = sw.empty_stack(len(jobs))
+    # multi-GPU: the local stack of the destination rank is a view into the gathered [world * n, N, N] stack
+    cg = sweep_mod.ChunkGather(local_rank, dst=0) if world > 1 else None
+    stack = cg.stack(counts, (grid, grid), sw.rdtype) if cg is not None else sw.empty_stack(len(jobs))
     host_ring = False
     try:
         host_stack = sw.empty_stack(len(jobs), host=True)
@@ -387,24 +396,48 @@ def run_ours(args):
     total_psf = len(jobs_all) * args.steps
     value = total_psf / (ms * 1e-3)
 
-    # ---- final gather of the PSF stack (the single collective; outside the per-step timing) -------
+    # ---- the single collective: gather of the PSF stack to rank 0 (paos_gather_psf, NCCL over NVLink) -------------
+    # (a) alone, after a sweep (gather_ms: what it costs when nothing hides it); (b) e2e_gathered: the sweep with the
+    # gather of every finished batch overlapped on a side stream, both inside the timed region
     gather_ms = gather_first_ms = None
+    e2e_gathered = None
     if world > 1:
-        sweep_mod.gather_stack(stack[:1], [1] * world, dst=0)  # first use builds NCCL's point-to-point connections
-        torch.cuda.synchronize()
-        # twice: the first call also pays rank 0's cudaMalloc of the [world * n, N, N] stack (hundreds of ms for 69 GB),
-        # the second one reuses that block from torch's caching allocator and shows the NVLink transfer itself
         gathers = []
-        for _ in range(2):
+        for _ in range(2):  # the first call builds NCCL's point-to-point connections
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
-            g0.record()
-            full = sweep_mod.gather_stack(stack, counts, dst=0)
-            g1.record()
+            g0.record(cg.stream)
+            cg.begin(stack, counts, chunk=max(counts))
+            ev = torch.cuda.Event()
+            ev.record()
+            cg.on_group(0, len(jobs), ev)
+            cg.finish()
+            g1.record(cg.stream)
             torch.cuda.synchronize()
             gathers.append(max_over_ranks(g0.elapsed_time(g1)))
-            del full
         gather_first_ms, gather_ms = gathers
+        barrier()
+        ms_g = max_over_ranks(timed_steps(torch, sw, jobs, stack, None, args.steps, extra_streams=[cg.stream],
+                                          before=lambda: cg.begin(stack, counts, chunk=sw.batch), after=cg.finish,
+                                          on_group=cg.on_group))
+        e2e_gathered = {"value": total_psf / (ms_g * 1e-3), "unit": UNIT + " (sweep + overlapped gather of every PSF to rank 0)",
+                        "gathered_bytes_per_step": int(sum(counts[1:]) * grid * grid * (8 if args.dtype == "complex128" else 4)),
+                        "gather_alone_ms": gather_ms}
+        barrier()
+
+    # ---- strong scaling (BASELINE.json configs[1] read literally: ONE 256-wavelength sweep sharded by wavelength) ----
+    strong = None
+    if world > 1:
+        base = jobs_all[: n_wl]  # field point 0
+        sblocks = sweep_mod.partition(base, world)
+        slo, shi = sblocks[rank]
+        sjobs = [dict(j) for j in base[slo:shi]]
+        sw.run(sjobs, out=stack[: len(sjobs)])
+        barrier()
+        ms_s = max_over_ranks(timed_steps(torch, sw, sjobs, stack[: len(sjobs)], None, args.steps))
+        strong = {"value": n_wl * args.steps / (ms_s * 1e-3), "unit": UNIT, "scaling": "strong",
+                  "psf_per_step": n_wl, "psf_per_gpu_per_step": len(sjobs), "ms_per_step": ms_s / args.steps}
+        barrier()
 
     # ---- end to end through the public API with host buffers ("e2e") -------------------------------
     sw.run(jobs, out=stack, host_out=host_stack)
@@ -412,6 +445,19 @@ def run_ours(args):
     ms_e2e = max_over_ranks(timed_steps(torch, sw, jobs, stack, host_stack, args.steps))
     e2e_value = total_psf / (ms_e2e * 1e-3)
     d2h = int(len(jobs) * grid * grid * (8 if args.dtype == "complex128" else 4))
+    barrier()
+
+    # ---- the same sweep with a reduced host product: the centred grid/4 window of every PSF as float32 (1 MiB instead of
+    # 32 MiB at 2048^2), cropped and narrowed on the device (paos_crop_convert) -----------------------------------------
+    win = grid // 4
+    small = torch.empty((len(jobs), win, win), dtype=torch.float32, pin_memory=True)
+    window = ((grid - win) // 2, (grid - win) // 2, win, win)
+    sw.run(jobs, out=stack, host_out=small, host_window=window)
+    barrier()
+    ms_red = max_over_ranks(timed_steps(torch, sw, jobs, stack, small, args.steps, host_window=window))
+    e2e_reduced = {"value": total_psf / (ms_red * 1e-3), "unit": UNIT + f" (centred {win}^2 float32 window of every PSF to host)",
+                   "d2h_bytes_per_step": int(len(jobs) * win * win * 4) * world}
+    del small
     barrier()
 
     # ---- the same sweep when its product is the encircled-energy curve of every PSF: the PSFs stay on the
@@ -592,9 +638,12 @@ def run_ours(args):
             "fft2_per_step": int(st1["fft2_recorded"] - st0["fft2_recorded"]) // args.steps * world,
             "pass_launches_per_psf": (st1["pass_launches"] - st0["pass_launches"]) / (len(jobs) * args.steps),
             "passes_per_psf": (st1["passes_planned"] - st0["passes_planned"]) / (len(jobs) * args.steps),
-            "e2e_ee": e2e_ee, "passes": passes, "gather_ms": gather_ms, "gather_first_ms": gather_first_ms,
+            "e2e_ee": e2e_ee, "e2e_reduced": e2e_reduced, "e2e_gathered": e2e_gathered, "strong_scaling": strong,
+            "passes": passes, "gather_ms": gather_ms, "gather_first_ms": gather_first_ms,
         }
         emit(line)
+    if cg is not None:
+        cg.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

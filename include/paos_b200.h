@@ -245,6 +245,26 @@ int paos_wfo_begin_record(paos_wfo *w);
 int paos_batch_execute(paos_wfo *const *ws, int nb);
 int paos_batch_chain_run(paos_wfo *const *ws, int nb, const paos_chain_args *args);
 
+/* ---- the single collective: gather of the per-GPU result stacks ---------------------------
+ * One process per GPU; propagation needs no communication, only the final stack (PSFs, or the much smaller encircled-energy
+ * curves) travels to one rank over NVLink.  NCCL is bound at run time (dlopen), so the library loads without it;
+ * PAOS_ERR_UNSUPPORTED when it is missing.  Messages of these four calls: paos_comm_last_error().
+ *   paos_comm_unique_id: 128 bytes identifying a new communicator (call on one rank, hand the bytes to the others by any
+ *     means, e.g. torch.distributed.broadcast_object_list);
+ *   paos_comm_create: collective over all ranks of the communicator;
+ *   paos_gather_psf: rank q contributes bytes_per_rank[q] bytes at local_dev; on `root` the block of rank q lands at
+ *     dst_dev + dst_offsets[q] (dst_offsets NULL: back to back in rank order).  A sweep gathers chunk by chunk -- the PSFs
+ *     of the batch that has just finished go to their final rows of the [sum of counts, N, N] stack while later
+ *     wavelengths still propagate.  bytes_per_rank (one entry per rank) must be the same on every rank.  Asynchronous on
+ *     `stream` (a cudaStream_t); calls on one communicator must be issued in the same order on every rank. */
+typedef struct paos_comm paos_comm;
+const char *paos_comm_last_error(void);
+int paos_comm_unique_id(void *id128);
+int paos_comm_create(paos_comm **out, const void *id128, int rank, int world, int device);
+int paos_comm_destroy(paos_comm *c);
+int paos_gather_psf(paos_comm *c, const void *local_dev, const size_t *bytes_per_rank, const size_t *dst_offsets, void *dst_dev,
+                    int root, void *stream);
+
 /* ---- the stand-alone polynomial classes (paos/classes/zernike.py:63-109 `Zernike`, :293-317 `cov`, :388-402 `PolyOrthoNorm`) ----
  * Polynomials at arbitrary points: rho, phi, mask (numpy masked-array convention, may be NULL) are host arrays of npoints
  * entries; points with rho > 1 or mask != 0 give 0.  norm may be NULL (ones).  nterms <= 64.
@@ -266,6 +286,19 @@ int paos_zernike_points(int device, int nterms, const int *m, const int *n, cons
  * on the handle's stream; the curve is 8*(nbins+1) bytes instead of the 8*n*n of the PSF (what a sweep gathers). */
 int paos_encircled_energy(paos_wfo *w, const void *psf_dev, double dx, double dy, double xc, double yc, double r_unit,
                           double r_max, int nbins, double *ee_dev_out);
+
+/* ---- Strehl ratio (docs/source/user/aberration/index.rst:27-45; documented by the reference, no code there) -------
+ * paos_psf_peak: out_dev[0] = value of the PSF at the optical axis (pixel (n/2, n/2)), out_dev[1] = its maximum; the Strehl
+ * ratio is the quotient of out_dev[0] for the aberrated and the ideal system.  psf_dev as for paos_encircled_energy.
+ * paos_screen_stats: mean, variance sigma_W^2 and pixel count of a wavefront-error screen (n*n device doubles, metres) over
+ * the pupil (x^2 + y^2)/radius^2 <= 1, x = (ix - n/2)*dx: the Marechal estimate is 1 - (2*pi/wl)^2 * sigma_W^2.
+ * Both asynchronous on the handle's stream, results in device memory (2 / 3 doubles). */
+int paos_psf_peak(paos_wfo *w, const void *psf_dev, double *out_dev);
+int paos_screen_stats(paos_wfo *w, const double *screen_dev, double radius, double dx, double dy, double *out_dev);
+/* Reduced host product of a sweep: copy the window [y0, y0+ny) x [x0, x0+nx) of an n*n real read-out (double for a
+ * complex128 handle, float for complex64) into a dense nx*ny device array, narrowed to float when to_float != 0.  A
+ * centred 512^2 float window of a 2048^2 PSF is 1 MiB instead of 32 MiB on the PCIe link.  Asynchronous. */
+int paos_crop_convert(paos_wfo *w, const void *src_dev, int x0, int y0, int nx, int ny, int to_float, void *dst_dev);
 
 /* ---- statistics -------------------------------------------------------------------------------- */
 typedef struct paos_stats {

@@ -97,6 +97,9 @@ def install_stubs():
     from loguru import logger
 
     logger.disable("paos")
+    # the repository's own `paos` shim (paos/: the drop-in import surface over paos_b200) must not answer for the reference
+    for name in [m for m in sys.modules if m == "paos" or m.startswith("paos.")]:
+        del sys.modules[name]
 
     pkg = types.ModuleType("paos")
     pkg.__path__ = [os.path.join(root, "paos")]

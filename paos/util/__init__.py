@@ -1,0 +1,1 @@
+"""``paos.util``: module paths of the reference (``paos/util/``) mapped onto ``paos_b200``."""

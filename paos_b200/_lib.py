@@ -78,6 +78,14 @@ SIGNATURES = {
     "paos_chain_run": (_i, [_vp, _d, _d, _d, _d, _d, _vp, _i, _vp, _i, C.POINTER(C.c_int), _vp]),
     "paos_zernike_points": (_i, [_i, _i, _ip, _ip, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp]),
     "paos_encircled_energy": (_i, [_vp, _vp, _d, _d, _d, _d, _d, _d, _i, _vp]),
+    "paos_psf_peak": (_i, [_vp, _vp, _vp]),
+    "paos_screen_stats": (_i, [_vp, _vp, _d, _d, _d, _vp]),
+    "paos_crop_convert": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "paos_comm_last_error": (C.c_char_p, []),
+    "paos_comm_unique_id": (_i, [_vp]),
+    "paos_comm_create": (_i, [C.POINTER(_vp), _vp, _i, _i, _i]),
+    "paos_comm_destroy": (_i, [_vp]),
+    "paos_gather_psf": (_i, [_vp, _vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), _vp, _i, _vp]),
     "paos_wfo_stats": (_i, [_vp, C.POINTER(PaosStats)]),
     "paos_wfo_enable_timing": (_i, [_vp, _i]),
     "paos_wfo_timing": (_i, [_vp, _dp, C.POINTER(C.c_uint64)]),
@@ -122,6 +130,19 @@ def check(rc):
     if rc == PAOS_ERR_UNSUPPORTED:
         raise NotImplementedError(msg)
     raise PaosError(msg)
+
+
+def check_comm(rc):
+    """Same for the communicator entry points (their messages come from paos_comm_last_error)."""
+    if rc == PAOS_OK:
+        return
+    msg = lib.paos_comm_last_error()
+    msg = msg.decode("utf-8", "replace") if msg else ""
+    if rc == PAOS_ERR_ARG:
+        raise ValueError(msg)
+    if rc == PAOS_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise PaosCudaError(msg)
 
 
 def device_count():

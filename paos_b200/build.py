@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 _TAG = os.environ.get("PAOS_BUILD_TAG", "")
 OBJ = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
 LIB = os.path.join(HERE, "libpaos_b200" + ("_" + _TAG if _TAG else "") + ".so")
-SOURCES = ["runtime.cu", "aux_kernels.cu", "pass_c128.cu", "pass_c64.cu"]
+SOURCES = ["runtime.cu", "aux_kernels.cu", "pass_c128.cu", "pass_c64.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v",
@@ -78,7 +78,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -670,4 +670,95 @@ cudaError_t launch_encircled_energy(const void* psf, int n, int real_is_float, d
     return cudaGetLastError();
 }
 
+// ---- Strehl ratio helpers (docs/source/user/aberration/index.rst:27-45) -----------------------------------------
+// (a) peak and centre value of a PSF (exact Strehl = centre irradiance of the aberrated PSF / that of the ideal one);
+// (b) mean and variance of a wavefront-error screen over the pupil rho <= 1 (Marechal: Strehl ~ 1 - k^2 sigma_W^2).
+// Single CTA of 1024 threads: both are O(N^2) reads of data that sits in L2 right after the pass that produced it, and a
+// fixed summation order keeps the result reproducible run to run.
+template <typename R>
+__global__ void __launch_bounds__(1024) psf_peak_kernel(const R* __restrict__ psf, int n, double* __restrict__ out) {
+    __shared__ double red[1024];
+    const size_t total = (size_t)n * n;
+    double mx = 0.0;
+    for (size_t i = threadIdx.x; i < total; i += 1024) mx = fmax(mx, (double)psf[i]);
+    red[threadIdx.x] = mx;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[0] = (double)psf[(size_t)(n / 2) * n + n / 2];  // x = y = 0 sits at pixel (n/2, n/2)
+        out[1] = red[0];
+    }
+}
+
+__global__ void __launch_bounds__(1024) screen_stats_kernel(const double* __restrict__ screen, int n, double inv_r2, double dx,
+                                                            double dy, double* __restrict__ out) {
+    __shared__ double r0[1024], r1[1024], r2[1024];
+    double s = 0.0, ss = 0.0, cnt = 0.0;
+    for (int iy = threadIdx.x >> 5; iy < n; iy += 32) {
+        const double y = (double)(iy - n / 2) * dy;
+        for (int ix = threadIdx.x & 31; ix < n; ix += 32) {
+            const double x = (double)(ix - n / 2) * dx;
+            if ((x * x + y * y) * inv_r2 <= 1.0) {
+                const double w = screen[(size_t)iy * n + ix];
+                s += w;
+                ss += w * w;
+                cnt += 1.0;
+            }
+        }
+    }
+    r0[threadIdx.x] = s;
+    r1[threadIdx.x] = ss;
+    r2[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int k = 512; k > 0; k >>= 1) {
+        if (threadIdx.x < k) {
+            r0[threadIdx.x] += r0[threadIdx.x + k];
+            r1[threadIdx.x] += r1[threadIdx.x + k];
+            r2[threadIdx.x] += r2[threadIdx.x + k];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double c = r2[0], mean = c > 0 ? r0[0] / c : 0.0;
+        out[0] = mean;
+        out[1] = c > 0 ? fmax(r1[0] / c - mean * mean, 0.0) : 0.0;  // variance sigma_W^2 over the pupil
+        out[2] = c;
+    }
+}
+
+cudaError_t launch_psf_peak(const void* psf, int n, int real_is_float, double* out, cudaStream_t st) {
+    if (real_is_float) psf_peak_kernel<float><<<1, 1024, 0, st>>>(reinterpret_cast<const float*>(psf), n, out);
+    else psf_peak_kernel<double><<<1, 1024, 0, st>>>(reinterpret_cast<const double*>(psf), n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_screen_stats(const double* screen, int n, double radius, double dx, double dy, double* out, cudaStream_t st) {
+    screen_stats_kernel<<<1, 1024, 0, st>>>(screen, n, 1.0 / (radius * radius), dx, dy, out);
+    return cudaGetLastError();
+}
+
+// ---- reduced host product: centred (or any) window of a real read-out, optionally narrowed to float ------------------
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) crop_convert_kernel(const S* __restrict__ src, int n, int x0, int y0, int nx, int ny, D* __restrict__ dst) {
+    const size_t total = (size_t)nx * ny;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int iy = (int)(i / nx), ix = (int)(i - (size_t)iy * nx);
+        dst[i] = (D)src[(size_t)(y0 + iy) * n + (x0 + ix)];
+    }
+}
+
+cudaError_t launch_crop_convert(const void* src, int n, int src_is_float, int x0, int y0, int nx, int ny, int dst_is_float, void* dst,
+                                cudaStream_t st) {
+    const size_t total = (size_t)nx * ny;
+    const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    if (src_is_float && dst_is_float) crop_convert_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)src, n, x0, y0, nx, ny, (float*)dst);
+    else if (src_is_float) crop_convert_kernel<float, double><<<blocks, 256, 0, st>>>((const float*)src, n, x0, y0, nx, ny, (double*)dst);
+    else if (dst_is_float) crop_convert_kernel<double, float><<<blocks, 256, 0, st>>>((const double*)src, n, x0, y0, nx, ny, (float*)dst);
+    else crop_convert_kernel<double, double><<<blocks, 256, 0, st>>>((const double*)src, n, x0, y0, nx, ny, (double*)dst);
+    return cudaGetLastError();
+}
+
 }  // namespace paosb

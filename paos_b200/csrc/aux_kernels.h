@@ -29,5 +29,9 @@ cudaError_t launch_psd_finalize(const void* f, int n, int dtype, const double* n
                                 double* out, cudaStream_t st);
 cudaError_t launch_encircled_energy(const void* psf, int n, int real_is_float, double dx, double dy, double xc, double yc,
                                     double inv_bin, int nbins, double* hist, double* ee, cudaStream_t st);
+cudaError_t launch_psf_peak(const void* psf, int n, int real_is_float, double* out, cudaStream_t st);
+cudaError_t launch_screen_stats(const double* screen, int n, double radius, double dx, double dy, double* out, cudaStream_t st);
+cudaError_t launch_crop_convert(const void* src, int n, int src_is_float, int x0, int y0, int nx, int ny, int dst_is_float, void* dst,
+                                cudaStream_t st);
 cudaError_t launch_normal(uint64_t seed, uint32_t stream_id, int n, double* out, cudaStream_t st);
 }  // namespace paosb

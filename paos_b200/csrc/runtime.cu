@@ -1601,6 +1601,41 @@ int paos_encircled_energy(paos_wfo* w, const void* psf_dev, double dx, double dy
     });
 }
 
+int paos_psf_peak(paos_wfo* w, const void* psf_dev, double* out_dev) {
+    if (!w || !psf_dev || !out_dev) return fail(PAOS_ERR_ARG, "null argument");
+    int rc = set_device(w);
+    if (rc) return rc;
+    const int n = w->n, is_float = w->dtype == PAOS_C128 ? 0 : 1;
+    return do_fn(w, 1, [=](cudaStream_t st) {
+        cudaError_t e = launch_psf_peak(psf_dev, n, is_float, out_dev, st);
+        return e == cudaSuccess ? PAOS_OK : fail(PAOS_ERR_CUDA, "peak launch failed: %s", cudaGetErrorString(e));
+    });
+}
+
+int paos_screen_stats(paos_wfo* w, const double* screen_dev, double radius, double dx, double dy, double* out_dev) {
+    if (!w || !screen_dev || !out_dev) return fail(PAOS_ERR_ARG, "null argument");
+    if (!(radius > 0) || !(dx > 0) || !(dy > 0)) return fail(PAOS_ERR_ARG, "radius, dx and dy must be positive");
+    int rc = set_device(w);
+    if (rc) return rc;
+    const int n = w->n;
+    return do_fn(w, 1, [=](cudaStream_t st) {
+        cudaError_t e = launch_screen_stats(screen_dev, n, radius, dx, dy, out_dev, st);
+        return e == cudaSuccess ? PAOS_OK : fail(PAOS_ERR_CUDA, "screen statistics launch failed: %s", cudaGetErrorString(e));
+    });
+}
+
+int paos_crop_convert(paos_wfo* w, const void* src_dev, int x0, int y0, int nx, int ny, int to_float, void* dst_dev) {
+    if (!w || !src_dev || !dst_dev) return fail(PAOS_ERR_ARG, "null argument");
+    if (x0 < 0 || y0 < 0 || nx < 1 || ny < 1 || x0 + nx > w->n || y0 + ny > w->n) return fail(PAOS_ERR_ARG, "window outside the grid");
+    int rc = set_device(w);
+    if (rc) return rc;
+    const int n = w->n, src_float = w->dtype == PAOS_C128 ? 0 : 1;
+    return do_fn(w, 1, [=](cudaStream_t st) {
+        cudaError_t e = launch_crop_convert(src_dev, n, src_float, x0, y0, nx, ny, to_float ? 1 : 0, dst_dev, st);
+        return e == cudaSuccess ? PAOS_OK : fail(PAOS_ERR_CUDA, "crop launch failed: %s", cudaGetErrorString(e));
+    });
+}
+
 int paos_wfo_stats(paos_wfo* w, paos_stats* out) {
     if (!w || !out) return fail(PAOS_ERR_ARG, "null argument");
     *out = w->stats;

@@ -2,9 +2,10 @@
 
 Same input dictionary (``conf``, ``light_output``, ``wfe``, ``debug``, ``return``, ``n_jobs``, ``store_keys``, ``save``,
 ``plot``); the ``joblib`` fan-out over wavelengths (``pipeline.py:140-150``) becomes a loop over one persistent device
-wavefront (or, with ``light_output``, a :class:`paos_b200.sweep.Sweep`).  The HDF5 writer and the plots of the reference
-(``saveOutput.py``, ``plot.py``) are outside this package: ``save`` / ``plot`` requests raise ``NotImplementedError``
-instead of being silently dropped, so pass ``save=False`` and keep the returned dictionaries.
+wavefront whose saved surfaces stream to pinned host memory while the chain continues (``run(async_snapshots=True)``).
+``save`` writes the reference's data cube through ``paos_b200.save_output`` (HDF5 when ``h5py`` is installed, else the
+same tree as ``.npz``); the plots (``plot.py``: matplotlib) are outside this package and ``plot=True`` raises
+``NotImplementedError`` instead of being silently dropped.
 """
 import logging
 
@@ -49,9 +50,11 @@ def pipeline(passvalue):
     passvalue.setdefault("n_jobs", 1)
     passvalue.setdefault("store_keys", "amplitude,dx,dy,wl")
     passvalue.setdefault("return", False)
-    if passvalue["save"] or passvalue["plot"]:
-        raise NotImplementedError("paos_b200.pipeline does not write HDF5 files or plots: pass save=False, plot=False and "
-                                  "return=True, and hand the dictionaries to the reference's save_datacube / plot_pop")
+    if passvalue["plot"]:
+        raise NotImplementedError("paos_b200.pipeline does not draw plots: pass plot=False and return=True, and hand the "
+                                  "dictionaries to the reference's plot_pop")
+    if passvalue["save"] and not passvalue.get("output"):
+        raise KeyError("output")  # the reference indexes passvalue['output'] (pipeline.py:163)
     pup, params, wavelengths, field, chains = setup_chains(passvalue)
     if passvalue.get("debug"):
         for line in raytrace(field, chains[0]):
@@ -59,8 +62,16 @@ def pipeline(passvalue):
     from .wfo import WFO
 
     keys = passvalue.get("device_keys")  # None: every array of every saved surface, like the reference's run
+    store_keys = passvalue["store_keys"].split(",") if passvalue["store_keys"] is not None else None
+    if keys is None and passvalue["save"] and not passvalue["return"] and store_keys is not None:
+        keys = store_keys  # nothing but the file is produced: read back only the arrays that will be stored
     wfo = WFO(pup, 1.0e-6 * wavelengths[0], params["grid_size"], params["zoom"], device=passvalue.get("device", 0),
               dtype=passvalue.get("dtype", "complex128"))
-    retval = [run(pup, 1.0e-6 * wl, params["grid_size"], params["zoom"], field, chain, wfo=wfo, keys=keys)
+    retval = [run(pup, 1.0e-6 * wl, params["grid_size"], params["zoom"], field, chain, wfo=wfo, keys=keys, async_snapshots=True)
               for wl, chain in zip(wavelengths, chains)]
+    if passvalue["save"]:
+        from .save_output import save_datacube
+
+        passvalue["written"] = save_datacube(retval, passvalue["output"], list(map(str, wavelengths)), keys_to_keep=store_keys,
+                                             overwrite=True)
     return retval if passvalue["return"] else None

@@ -32,6 +32,40 @@ def push_results(wfo, keys=None):
     return out
 
 
+class AsyncSnapshots:
+    """Saved surfaces without stalling the chain (the device half of the reference's output path, ``saveOutput.py`` /
+    ``pipeline.py:72-84``): every requested array of a ``save=True`` surface is read out on the device
+    (``paos_wfo_read_device``: fused into the pass that produces the surface) and copied to pinned host memory
+    asynchronously on the wavefront's stream, while the host goes on recording the next surfaces.  The arrays handed out
+    are numpy views of those pinned buffers; they hold valid data once :meth:`finish` has returned."""
+
+    _DEVICE_READ = {"amplitude": "amplitude_device", "phase": "phase_device", "wfo": "wfo_device"}
+
+    def __init__(self, wfo):
+        self.wfo = wfo
+
+    def take(self, keys=None):
+        import torch
+
+        wfo = self.wfo
+        want = ARRAY_KEYS if keys is None else tuple(k for k in ARRAY_KEYS if k in keys)
+        out = {}
+        for k in want:
+            dev = getattr(wfo, self._DEVICE_READ[k])()
+            host = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)
+            with torch.cuda.stream(wfo._stream):
+                host.copy_(dev, non_blocking=True)
+            out[k] = host.numpy()
+        out.update(
+            wz=wfo.wz, distancetofocus=wfo.distancetofocus, fratio=wfo.fratio, dx=wfo.dx, dy=wfo.dy, wl=wfo.wl,
+            extent=wfo.extent, propagator=wfo.propagator,
+        )
+        return out
+
+    def finish(self):
+        self.wfo.sync()
+
+
 def _surface_aperture(wfo, item, vt, vs):
     ap = item["aperture"]
     xc = ap["xc"] if np.isfinite(ap["xc"]) else vs[0]
@@ -45,7 +79,7 @@ def _surface_aperture(wfo, item, vt, vs):
 
 
 def run(pupil_diameter, wavelength, gridsize, zoom, field, opt_chain, *, device=0, dtype="complex128",
-        stream=None, keys=None, psd_noise=None, wfo=None, snapshot=None):
+        stream=None, keys=None, psd_noise=None, wfo=None, snapshot=None, async_snapshots=False):
     """Run the physical-optics propagation of one wavelength / field through ``opt_chain``.
 
     Positional parameters and the returned ``{surface_num: {...}}`` dictionary are the reference's.  Keyword-only
@@ -53,7 +87,9 @@ def run(pupil_diameter, wavelength, gridsize, zoom, field, opt_chain, *, device=
     saved surface (e.g. ``("amplitude",)``, the reference pipeline's ``store_keys``); ``psd_noise`` is a callable
     ``(surface_num, shape) -> (n1, n2)`` injecting the PSD noise draws (bit-parity mode); ``wfo`` re-uses an
     existing :class:`WFO` (its buffer and stream) instead of allocating one; ``snapshot`` replaces
-    :func:`push_results` for saved surfaces, e.g. to keep read-outs on the device (``snapshot(wfo, item) -> dict``).
+    :func:`push_results` for saved surfaces, e.g. to keep read-outs on the device (``snapshot(wfo, item) -> dict``);
+    ``async_snapshots`` streams the saved arrays to pinned host memory while the chain continues (:class:`AsyncSnapshots`;
+    same values, the result dictionaries hold views of pinned buffers).
     """
     assert isinstance(opt_chain, dict), "opt_chain must be a dict"
     results = {}
@@ -65,6 +101,7 @@ def run(pupil_diameter, wavelength, gridsize, zoom, field, opt_chain, *, device=
     else:
         assert wfo.grid_size == gridsize, "the re-used WFO has a different grid size"
         wfo.reset(pupil_diameter, wavelength, zoom)
+    streamer = AsyncSnapshots(wfo) if (async_snapshots and snapshot is None) else None
 
     for item in opt_chain.values():
         if item["type"] == "Coordinate Break":
@@ -99,7 +136,10 @@ def run(pupil_diameter, wavelength, gridsize, zoom, field, opt_chain, *, device=
                 snap["wfe"] = wfe
 
         if save:
-            snap.update(push_results(wfo, keys) if snapshot is None else snapshot(wfo, item))
+            if streamer is not None:
+                snap.update(streamer.take(keys))
+            else:
+                snap.update(push_results(wfo, keys) if snapshot is None else snapshot(wfo, item))
 
         abcd_t, abcd_s = item["ABCDt"], item["ABCDs"]
         Ms, Mt = abcd_s.M, abcd_t.M
@@ -121,6 +161,8 @@ def run(pupil_diameter, wavelength, gridsize, zoom, field, opt_chain, *, device=
         total_s = abcd_s * total_s
         if save:
             snap["ABCDt"], snap["ABCDs"] = total_t, total_s
-            results[item["num"]] = deepcopy(snap) if snapshot is None else snap
+            results[item["num"]] = deepcopy(snap) if (snapshot is None and streamer is None) else snap
 
+    if streamer is not None:
+        streamer.finish()
     return results

@@ -126,7 +126,7 @@ class Sweep:
         return torch.empty((count, self.n, self.n), dtype=self.rdtype, device=self.tdev)
 
     def run(self, jobs, out=None, host_out=None, psd_noise=None, native=True, cache_compiled=True, threads=True,
-            ee=None, ee_out=None, ee_host_out=None):
+            ee=None, ee_out=None, ee_host_out=None, host_window=None, peak_out=None, on_group=None):
         """Propagate ``jobs``; the last saved surface of job k is read out (``what``) into ``out[k]``.
 
         ``ee``: ``dict(r_max=..., nbins=...)`` also reduces every PSF (``what="psf"``) to its encircled-energy curve on the
@@ -140,6 +140,12 @@ class Sweep:
         which only suits a consumer that reads after the sweep).  ``native``: run each chain through ``paos_chain_run`` /
         ``paos_batch_chain_run`` (C++ per-surface loop) instead of the Python driver; ``cache_compiled=False`` rebuilds
         the native surface records of every job on every call.
+        ``host_window``: ``(x0, y0, nx, ny)`` -- ``host_out`` then receives only that window of every read-out, narrowed to
+        ``host_out``'s dtype (``paos_crop_convert``: a centred 512^2 float32 window of a 2048^2 PSF is 1 MiB on the PCIe link
+        instead of 32 MiB).  ``peak_out``: ``[len(jobs), 2]`` float64 device tensor receiving the on-axis value and the
+        maximum of every read-out (``paos_psf_peak``, the numerator of a Strehl ratio).  ``on_group(first_job, stop_job,
+        event)``: called from the slot's thread after each batch has been enqueued, with a CUDA event recorded behind it
+        (used to overlap the gather of finished PSFs with the rest of the sweep).
         Returns ``(out, meta)`` with one ``meta`` dict of host scalars per job, after all device work has completed.
         """
         import ctypes as C
@@ -166,6 +172,18 @@ class Sweep:
         from . import chain as chain_mod
 
         meta = [None] * len(jobs)
+        stage = None
+        if host_window is not None:
+            if host_out is None:
+                raise ValueError("host_window needs host_out")
+            x0, y0, nx, ny = (int(v) for v in host_window)
+            if tuple(host_out.shape[1:]) != (ny, nx) or host_out.dtype not in (torch.float32, torch.float64):
+                raise ValueError(f"host_out must be [rows, {ny}, {nx}] float32 or float64")
+            key = (nx, ny, host_out.dtype)
+            if getattr(self, "_stage_key", None) != key:
+                self._stage = [[torch.empty((ny, nx), dtype=host_out.dtype, device=self.tdev) for _ in range(B)] for _ in range(nslots)]
+                self._stage_key = key
+            stage = self._stage
 
         def compile_native(k, job):
             """Compiled chain of job k with its read-out wired to out[k], or None when the native runner cannot take it."""
@@ -199,8 +217,10 @@ class Sweep:
             last = res[max(res.keys())] if res else {}
             return {k2: v for k2, v in last.items() if k2 not in ("aperture", "wfe")}
 
-        def finish(k, job, wfo, stream, last):
+        def finish(k, job, wfo, stream, last, s=0, i=0):
             dst = out[k % out.shape[0]]
+            if peak_out is not None:
+                _lib.check(_lib.lib.paos_psf_peak(wfo._handle, C.c_void_p(dst.data_ptr()), C.c_void_p(peak_out[k].data_ptr())))
             last["tag"] = job.get("tag", str(k))
             meta[k] = last
             if ee is not None:
@@ -211,6 +231,11 @@ class Sweep:
                     with torch.cuda.stream(stream):
                         ee_host_out[k].copy_(ee_out[k], non_blocking=True)
             if host_out is not None:
+                if stage is not None:
+                    st = stage[s][i]
+                    _lib.check(_lib.lib.paos_crop_convert(wfo._handle, C.c_void_p(dst.data_ptr()), x0, y0, nx, ny,
+                                                          1 if host_out.dtype == torch.float32 else 0, C.c_void_p(st.data_ptr())))
+                    dst = st
                 with torch.cuda.stream(stream):
                     host_out[k % host_out.shape[0]].copy_(dst, non_blocking=True)
 
@@ -237,7 +262,11 @@ class Sweep:
             for i, k in enumerate(ks):
                 if lasts[i] is None:
                     lasts[i] = python_driver(k, jobs[k], wfos[i])
-                finish(k, jobs[k], wfos[i], stream, lasts[i])
+                finish(k, jobs[k], wfos[i], stream, lasts[i], s, i)
+            if on_group is not None:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                on_group(ks[0], ks[-1] + 1, ev)
 
         groups = [list(range(g, min(g + B, len(jobs)))) for g in range(0, len(jobs), B)]
 
@@ -336,3 +365,134 @@ def gather_stack(local, counts, dst=0, group=None):
         return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
     dist.gather(pad, gather_list=None, dst=dst, group=group)
     return None
+
+
+def chunk_schedule(counts, chunk, row_bytes):
+    """The chunked gather as every rank must issue it: one entry per chunk g (jobs [g*chunk, (g+1)*chunk) of every rank's
+    block) with the bytes each rank contributes and the byte offset of its rows in the destination stack, which holds the
+    ranks' blocks back to back in rank order.  Ranks with fewer jobs contribute zero bytes to the last chunks (ragged
+    blocks), so that the sequence of collective calls is the same everywhere."""
+    counts = [int(c) for c in counts]
+    chunk = max(1, int(chunk))
+    base = [sum(counts[:q]) for q in range(len(counts))]
+    out = []
+    for g in range((max(counts) + chunk - 1) // chunk if counts else 0):
+        lo = g * chunk
+        sizes = [max(0, min(c, lo + chunk) - lo) * row_bytes for c in counts]
+        offs = [(b + lo) * row_bytes for b in base]
+        out.append((lo, sizes, offs))
+    return out
+
+
+class ChunkGather:
+    """The sweep's one collective, overlapped with the sweep: every finished batch of PSFs is sent to its final rows of the
+    destination stack on rank ``dst`` (``paos_gather_psf``: grouped NCCL send / receive over NVLink on a side stream) while
+    later wavelengths still propagate.  Usage on every rank::
+
+        cg = ChunkGather(device)                      # once: builds the communicator (collective)
+        cg.begin(stack, counts, chunk=sweep.batch)    # per sweep: stack = local [n_local, N, N] device tensor
+        sweep.run(jobs, out=stack, on_group=cg.on_group)
+        full = cg.finish()                            # [sum(counts), N, N] on rank dst, None elsewhere
+
+    NCCL calls of one communicator must be issued in the same order everywhere, so a single pump thread per rank sends the
+    chunks in index order, whatever order the slots finish them in.
+    """
+
+    def __init__(self, device, dst=0, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.C = torch, C
+        self.rank, self.world, self.dst = dist.get_rank(group), dist.get_world_size(group), int(dst)
+        self.device = int(device)
+        ident = [None]
+        if self.rank == 0:
+            buf = (C.c_char * 128)()
+            _lib.check_comm(_lib.lib.paos_comm_unique_id(C.cast(buf, C.c_void_p)))
+            ident[0] = bytes(buf.raw)
+        dist.broadcast_object_list(ident, src=0, group=group)
+        h = C.c_void_p()
+        idbuf = C.create_string_buffer(ident[0], 128)
+        torch.cuda.set_device(self.device)
+        _lib.check_comm(_lib.lib.paos_comm_create(C.byref(h), C.cast(idbuf, C.c_void_p), self.rank, self.world, self.device))
+        self._comm = h
+        self.stream = torch.cuda.Stream(device=torch.device("cuda", self.device))
+        self._full = None
+
+    def stack(self, counts, row_shape, dtype):
+        """Local result stack ``[counts[rank], *row_shape]``.  On the destination rank it is a view into the full
+        ``[sum(counts), *row_shape]`` stack at the rank's own offset, so its own block never has to be copied."""
+        torch = self.torch
+        dev = torch.device("cuda", self.device)
+        counts = [int(c) for c in counts]
+        if self.rank != self.dst:
+            return torch.empty((counts[self.rank],) + tuple(row_shape), dtype=dtype, device=dev)
+        self._full = torch.empty((sum(counts),) + tuple(row_shape), dtype=dtype, device=dev)
+        lo = sum(counts[: self.rank])
+        return self._full[lo: lo + counts[self.rank]]
+
+    def close(self):
+        h, self._comm = self._comm, None
+        if h is not None:
+            _lib.lib.paos_comm_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def begin(self, local, counts, chunk):
+        import threading
+
+        torch = self.torch
+        self.local, self.counts, self.chunk = local, [int(c) for c in counts], max(1, int(chunk))
+        self.row_bytes = local[0].numel() * local.element_size() if local.shape[0] else 0
+        total = sum(self.counts)
+        if self.rank == self.dst:
+            if self._full is None or tuple(self._full.shape) != (total,) + tuple(local.shape[1:]) or self._full.dtype != local.dtype:
+                self._full = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        self.schedule = chunk_schedule(self.counts, self.chunk, self.row_bytes)
+        self._events = {}
+        self._cv = threading.Condition()
+        self._error = None
+        self._thread = threading.Thread(target=self._pump, daemon=True)
+        self._thread.start()
+
+    def on_group(self, lo, hi, event):
+        """Callback for ``Sweep.run(on_group=...)``: jobs [lo, hi) of the local block are done once ``event`` has fired."""
+        with self._cv:
+            self._events[lo // self.chunk] = event
+            self._cv.notify_all()
+
+    def _pump(self):
+        C, torch = self.C, self.torch
+        try:
+            torch.cuda.set_device(self.device)
+            mine = self.counts[self.rank]
+            for g, (lo, nbytes, offsets) in enumerate(self.schedule):
+                if lo < mine:
+                    with self._cv:
+                        while g not in self._events:
+                            self._cv.wait()
+                        ev = self._events[g]
+                    self.stream.wait_event(ev)
+                sizes = (C.c_size_t * self.world)()
+                offs = (C.c_size_t * self.world)()
+                for q in range(self.world):
+                    sizes[q], offs[q] = nbytes[q], offsets[q]
+                src = self.local[lo].data_ptr() if lo < mine else None
+                dstp = self._full.data_ptr() if self.rank == self.dst else None
+                _lib.check_comm(_lib.lib.paos_gather_psf(self._comm, C.c_void_p(src), sizes, offs, C.c_void_p(dstp), self.dst,
+                                                         C.c_void_p(self.stream.cuda_stream)))
+        except Exception as exc:  # surfaced by finish()
+            self._error = exc
+
+    def finish(self):
+        self._thread.join()
+        if self._error is not None:
+            raise self._error
+        self.stream.synchronize()
+        return self._full if self.rank == self.dst else None

@@ -185,6 +185,9 @@ class WFO:
     def psf_device(self):
         return self._read_device(_lib.READ_PSF)
 
+    def phase_device(self):
+        return self._read_device(_lib.READ_PHASE)
+
     def wfo_device(self):
         return self._read_device(_lib.READ_WFO)
 

@@ -118,6 +118,66 @@ def _gloo_worker(rank, world, port, tmp):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("counts,chunk", [([4, 4], 2), ([5, 3], 2), ([3, 0, 7], 4), ([1, 1, 1, 1], 8), ([6], 4)])
+def test_chunk_schedule_covers_every_row_once(counts, chunk):
+    """The overlapped gather (ChunkGather) sends chunk g of every rank to its final rows: together the chunks must place
+    every PSF exactly once, in rank order, for equal and ragged blocks."""
+    from paos_b200.sweep import chunk_schedule
+
+    rng = np.random.default_rng(1)
+    locals_ = [rng.standard_normal((c, 3, 3)) for c in counts]
+    if all(c == 0 for c in counts):
+        return
+    ref = [a for a in locals_ if len(a)]
+    row = ref[0][0].nbytes
+    locals_ = [a if len(a) else np.zeros((0, 3, 3)) for a in locals_]
+    full = np.zeros(sum(counts) * row, dtype=np.uint8)
+    covered = np.zeros(sum(counts), dtype=int)
+    for lo, sizes, offs in chunk_schedule(counts, chunk, row):
+        assert len(sizes) == len(offs) == len(counts)
+        for q, loc in enumerate(locals_):
+            if sizes[q]:
+                assert sizes[q] % row == 0 and offs[q] % row == 0
+                full[offs[q]: offs[q] + sizes[q]] = loc.view(np.uint8).reshape(-1)[lo * row: lo * row + sizes[q]]
+                covered[offs[q] // row: (offs[q] + sizes[q]) // row] += 1
+    assert np.all(covered == 1)
+    assert np.array_equal(full.view(np.float64).reshape(-1, 3, 3), np.concatenate(locals_, axis=0))
+
+
+def _gloo_schedule_worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+
+    from paos_b200.sweep import chunk_schedule, partition
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        jobs = [{"opt_chain": {}} for _ in range(11)]
+        blocks = partition(jobs, world)
+        counts = [b - a for a, b in blocks]
+        sched = chunk_schedule(counts, 4, 128)
+        # every rank must issue the same sequence of collective calls: compare the schedules
+        mine = torch.tensor([v for lo, sizes, offs in sched for v in [lo] + sizes + offs], dtype=torch.int64)
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        assert all(torch.equal(g, mine) for g in gathered)
+        if rank == 0:
+            open(os.path.join(tmp, "ok2"), "w").write("ok")
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_chunk_schedule_agrees_across_ranks_gloo(tmp_path):
+    import torch.multiprocessing as mp
+
+    port = 29900 + os.getpid() % 90
+    mp.spawn(_gloo_schedule_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok2")
+
+
 def test_gather_stack_world_size_2_gloo(tmp_path):
     import torch.multiprocessing as mp
 
