@@ -142,6 +142,19 @@ int paos_wfo_zernike_masked(paos_wfo *w, int nterms, const int *m, const int *n,
 int paos_zernike_cov(paos_wfo *w, int nterms, const int *m, const int *n, const double *norm, double radius,
                      double dx, double dy, double offset, int origin, const unsigned char *host_mask,
                      double *cov_host_out);
+/* wfo.py:656-871 (grid_sag) in full: the raw map (ny x nx host doubles at pitch delx x dely, decentred by xdec, ydec pixels;
+ * host_mask: optional ny*nx bytes, non-zero = masked, NULL = mask the non-finite and the zero samples like the reference)
+ * is masked, recentred by a Fourier shift, padded / cropped to the WFO extent and resampled to the pitch (dx, dy) of the
+ * wavefront with cubic B-splines and Gaussian anti-aliasing -- all on the device (csrc/sag_kernels.cu) -- then applied as
+ * exp(2*pi*i*sag/wl) with masked pixels at 0.  screen_host_out / mask_host_out: optional n*n doubles / bytes receiving the
+ * resampled map and its mask.  Blocks the host until the map is ready (input preparation, not the per-wavelength path). */
+int paos_wfo_grid_sag(paos_wfo *w, const double *host_sag, const unsigned char *host_mask, int nx, int ny, double delx,
+                      double dely, double xdec, double ydec, double dx, double dy, double wl, double *screen_host_out,
+                      unsigned char *mask_host_out);
+int paos_grid_sag_cache_clear(void);
+/* impulse response of scipy.ndimage.fourier_shift along an axis of n samples (what paos_wfo_grid_sag convolves with);
+ * host-only helper exported for the CPU tests */
+int paos_fourier_shift_kernel(int n, double shift, double *re_out, double *im_out);
 /* wfo.py:873-949 + psd.py:113-148: surface-error screen with power spectrum A/(B+(f/fknee)^C) between
  * fmin and fmax plus white roughness SR, times 2*unit_scale, applied as a phase screen.
  * noise1/noise2: n*n host doubles replacing the reference's two np.random.randn draws (bit-parity
@@ -172,7 +185,8 @@ enum {
     PAOS_SURF_COORDBREAK = 1,
     PAOS_SURF_ZERNIKE = 2,
     PAOS_SURF_SCREEN = 3,    /* Grid Sag already on the WFO grid (metres, 0 where masked)           */
-    PAOS_SURF_PSD = 4
+    PAOS_SURF_PSD = 4,
+    PAOS_SURF_GRIDSAG = 5    /* Grid Sag as the lens file gives it: raw map, resampled on the device at the surface's pitch */
 };
 typedef struct paos_surface {
     int type;
@@ -201,6 +215,15 @@ typedef struct paos_surface {
     const double *screen;                       /* PAOS_SURF_SCREEN: n*n doubles (host, or device if flagged) */
     const double *psd_noise1, *psd_noise2;      /* host arrays or NULL (device RNG from psd_seed)        */
     void *read_dst;                             /* device destination of the read-out                    */
+    /* PAOS_SURF_GRIDSAG (wfo.py:656-871): sag = sag_ny x sag_nx host doubles in metres, sag_mask = optional bytes (non-zero =
+     * masked; NULL = mask non-finite and zero samples), pitch sag_delx x sag_dely, decentre sag_xdec, sag_ydec pixels.
+     * sag_key != 0 identifies the map's content: jobs that carry the same key (one map, many wavelengths) share the
+     * prepared screen whenever the pitch at the surface is the same (paos_grid_sag_cache_clear releases them). */
+    const double *sag;
+    const unsigned char *sag_mask;
+    int sag_nx, sag_ny;
+    double sag_delx, sag_dely, sag_xdec, sag_ydec;
+    uint64_t sag_key;
 } paos_surface;
 typedef struct paos_snapshot {
     int surface;           /* index into the surface array */

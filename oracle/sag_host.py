@@ -1,14 +1,17 @@
-"""Host-side preparation of a Grid Sag map (input artefact, not the wavefront): masking, sub-pixel recentring and
+"""TEST INFRASTRUCTURE (oracle): host statement of the decision flow of ``paos_wfo_grid_sag`` (``csrc/runtime.cu``) over the
+separable operators of ``oracle/separable_resample.py``; until round 2 the product's own host path.  Only ``tests/`` import it.
+
+Host-side preparation of a Grid Sag map (input artefact, not the wavefront): masking, sub-pixel recentring and
 padding / cropping to the WFO grid extent, as in steps 1-2 of ``paos/classes/wfo.py:753-845``.  What reaches the device
 is an ``N x N`` float64 screen (0 where masked) that ``paos_wfo_phase_screen`` applies in the fused passes.
 
 Steps 3-4 of the reference (cubic-spline ``rescale`` / ``resize`` with anti-aliasing, ``wfo.py:848-862``) and the
-up-sampling by 2 for an odd pad / crop difference (``:806-814``) use ``paos_b200/resample.py``, the host-side
+up-sampling by 2 for an odd pad / crop difference (``:806-814``) use ``oracle/separable_resample.py``, the host-side
 restatement of the scikit-image 0.24 routines the reference calls (parity unpinned: scikit-image is not available here).
 """
 import numpy as np
 
-from .resample import rescale, resize
+from oracle.separable_resample import rescale, resize
 
 MAX_MAP_ELEMENTS = 1 << 28  # 2 GiB of float64 per intermediate map: beyond this the pitch is wrong for this grid
 

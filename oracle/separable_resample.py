@@ -1,4 +1,6 @@
-"""Host-side cubic resampling of a grid-sag map onto the WFO pixel pitch (input preparation, not the wavefront).
+"""TEST INFRASTRUCTURE (oracle): host statement, operator by operator, of the separable resampler that the device runs
+(``paos_b200/csrc/sag_kernels.cu``): cubic resampling of a grid-sag map onto the WFO pixel pitch.  Only ``tests/`` import it;
+until round 2 it was the product's host-side resampler.
 
 The reference resamples the map with ``skimage.transform.rescale`` / ``resize`` (``order=3``, explicit
 ``anti_aliasing``; ``paos/classes/wfo.py:696-751``, called at ``:813-814, :851, :856-862``).  scikit-image 0.24 implements
@@ -6,7 +8,8 @@ both as: optional Gaussian pre-filter with ``sigma = max(0, (in/out - 1)/2)`` pe
 the pixel-centre-aligned coordinates ``(o + 1/2)*in/out - 1/2`` with whole-sample-symmetric ("mirror") boundaries, and a
 final clip to the input range.  Everything is separable, so it is written here as per-axis operators: a symmetric FIR,
 the B-spline recursive pre-filter, and a sparse 4-tap interpolation matrix -- the form a device version would take (two
-small banded products per map).  ``tests/test_host_logic.py`` holds it against the oracle's scipy restatement.
+small banded products per map).  ``tests/test_host_logic.py`` holds it against the oracle's scipy restatement (``oracle/skimage_np.py``) and
+``tests/test_gpu_sag.py`` holds the device kernels against both.
 """
 import numpy as np
 

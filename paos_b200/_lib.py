@@ -67,6 +67,9 @@ SIGNATURES = {
     "paos_wfo_zernike": (_i, [_vp, _i, _ip, _ip, _dp, _d, _d, _d, _d, _i, _d, _vp]),
     "paos_wfo_zernike_masked": (_i, [_vp, _i, _ip, _ip, _dp, _d, _d, _d, _d, _i, _d, _vp, _vp]),
     "paos_zernike_cov": (_i, [_vp, _i, _ip, _ip, _vp, _d, _d, _d, _d, _i, _vp, _vp]),
+    "paos_wfo_grid_sag": (_i, [_vp, _vp, _vp, _i, _i, _d, _d, _d, _d, _d, _d, _d, _vp, _vp]),
+    "paos_fourier_shift_kernel": (_i, [_i, _d, _vp, _vp]),
+    "paos_grid_sag_cache_clear": (_i, []),
     "paos_wfo_psd": (_i, [_vp, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d, _vp, _vp, C.c_uint64, _vp]),
     "paos_wfo_ptp": (_i, [_vp, _d, _d, _d, _d]),
     "paos_wfo_stw": (_i, [_vp, _d, _d, _d, _d]),

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 _TAG = os.environ.get("PAOS_BUILD_TAG", "")
 OBJ = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
 LIB = os.path.join(HERE, "libpaos_b200" + ("_" + _TAG if _TAG else "") + ".so")
-SOURCES = ["runtime.cu", "aux_kernels.cu", "pass_c128.cu", "pass_c64.cu", "comm.cu"]
+SOURCES = ["runtime.cu", "aux_kernels.cu", "pass_c128.cu", "pass_c64.cu", "comm.cu", "sag_kernels.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v",

@@ -10,9 +10,9 @@ import numpy as np
 from . import _lib
 from .zernike import j2mn, zernike_norms
 
-SURF_GENERIC, SURF_COORDBREAK, SURF_ZERNIKE, SURF_SCREEN, SURF_PSD = 0, 1, 2, 3, 4
+SURF_GENERIC, SURF_COORDBREAK, SURF_ZERNIKE, SURF_SCREEN, SURF_PSD, SURF_GRIDSAG = 0, 1, 2, 3, 4, 5
 _TYPES = {"Standard": SURF_GENERIC, "Paraxial Lens": SURF_GENERIC, "ABCD": SURF_GENERIC,
-          "Coordinate Break": SURF_COORDBREAK, "Zernike": SURF_ZERNIKE, "Grid Sag": SURF_SCREEN, "PSD": SURF_PSD}
+          "Coordinate Break": SURF_COORDBREAK, "Zernike": SURF_ZERNIKE, "Grid Sag": SURF_GRIDSAG, "PSD": SURF_PSD}
 _SHAPES = {"elliptical": _lib.SHAPE_ELLIPSE, "rectangular": _lib.SHAPE_RECT}
 
 
@@ -28,6 +28,9 @@ class Surface(C.Structure):
         ("zernike_m", C.POINTER(C.c_int)), ("zernike_n", C.POINTER(C.c_int)), ("zernike_coef", C.POINTER(C.c_double)),
         ("screen", C.POINTER(C.c_double)), ("psd_noise1", C.POINTER(C.c_double)), ("psd_noise2", C.POINTER(C.c_double)),
         ("read_dst", C.c_void_p),
+        ("sag", C.POINTER(C.c_double)), ("sag_mask", C.POINTER(C.c_ubyte)), ("sag_nx", C.c_int), ("sag_ny", C.c_int),
+        ("sag_delx", C.c_double), ("sag_dely", C.c_double), ("sag_xdec", C.c_double), ("sag_ydec", C.c_double),
+        ("sag_key", C.c_uint64),
     ]
 
 
@@ -66,18 +69,11 @@ class CompiledChain:
         self.keep = []
         self.nums = []
         self.saved = []
-        init_pitch = True  # no surface so far can have changed the pixel pitch (no propagation, no magnification)
-        has_sag = any(item["type"] == "Grid Sag" for item in items)  # only then is the pitch worth tracking
         for i, item in enumerate(items):
             s = self.array[i]
             kind = item["type"]
             if kind not in _TYPES:
                 raise ValueError(f"Surface Type not recognised: {kind}")
-            if kind == "Grid Sag" and not init_pitch:
-                # wfo.py:848-862 resamples the map to the pitch *at the surface*, which only the scalar walk knows
-                raise NotImplementedError("Grid Sag behind a propagation or magnification: use the Python driver")
-            if has_sag and (item["ABCDt"].thickness != 0 or item["ABCDt"].M != 1 or item["ABCDs"].M != 1):
-                init_pitch = False
             s.type = _TYPES[kind]
             s.is_stop = 1 if item["is_stop"] else 0
             s.save = 1 if item["save"] else 0
@@ -118,28 +114,18 @@ class CompiledChain:
                 s.zernike_n = n32.ctypes.data_as(C.POINTER(C.c_int))
                 s.zernike_coef = coef.ctypes.data_as(C.POINTER(C.c_double))
                 s.zernike_radius = float(item["Zradius"])
-            elif s.type == SURF_SCREEN:
-                screen = _on_grid_sag(item, self.n, pupil_diameter, zoom)
-                s.screen_dx = s.screen_dy = pupil_diameter * zoom / self.n
-                if device is None:
-                    self.keep.append(screen)
-                    s.screen = screen.ctypes.data_as(C.POINTER(C.c_double))
-                else:
-                    # upload once and share between jobs that carry the same map (one per wavelength in a sweep)
-                    import torch
-
-                    import hashlib
-
-                    key = (screen.shape, int(device), hashlib.sha1(screen.tobytes()).hexdigest())
-                    cache = screen_cache if screen_cache is not None else {}
-                    dev = cache.get(key)
-                    if dev is None:
-                        dev = torch.from_numpy(screen).to(torch.device("cuda", int(device)))
-                        torch.cuda.synchronize(int(device))
-                        cache[key] = dev
-                    self.keep.append(dev)
-                    s.screen = C.cast(C.c_void_p(dev.data_ptr()), C.POINTER(C.c_double))
-                    s.screen_on_device = 1
+            elif s.type == SURF_GRIDSAG:
+                # the raw map travels as the lens file gives it; the library resamples it on the device at the pitch the
+                # beam has at this surface (wfo.py:848-862), and jobs that carry the same map share the prepared screen
+                data, mask, key = _raw_sag(item, screen_cache)
+                self.keep += [data, mask]
+                s.sag = data.ctypes.data_as(C.POINTER(C.c_double))
+                if mask is not None:
+                    s.sag_mask = mask.ctypes.data_as(C.POINTER(C.c_ubyte))
+                s.sag_nx, s.sag_ny = int(item["nx"]), int(item["ny"])
+                s.sag_delx, s.sag_dely = float(item["delx"]), float(item["dely"])
+                s.sag_xdec, s.sag_ydec = float(item["xdec"]), float(item["ydec"])
+                s.sag_key = key
             elif s.type == SURF_PSD:
                 from .wfo import _unit_to_m
 
@@ -165,15 +151,31 @@ class CompiledChain:
         s.read_discard = 1 if final else 0
 
 
-def _on_grid_sag(item, n, pupil_diameter, zoom):
-    """Screen (metres, 0 where masked) of a Grid Sag surface at INIT sampling (``paos_b200/sag.py``); the native runner
-    takes surfaces that precede any change of sampling, which is where lens files put them."""
-    from .sag import prepare_sag
+def _raw_sag(item, cache):
+    """``(data, mask, key)`` of a Grid Sag item: contiguous float64 samples (masked ones as 0), the explicit mask of a masked
+    array as bytes (None: the library masks non-finite and zero samples, wfo.py:757-765) and a 64-bit content key.  The
+    digest is computed once per map object (``cache``: id of the array -> result, kept by the Sweep)."""
+    import hashlib
 
-    d = pupil_diameter * zoom / n
-    screen, _ = prepare_sag(item["grid_sag"], int(item["nx"]), int(item["ny"]), item["delx"], item["dely"], item["xdec"],
-                            item["ydec"], n, d, d)
-    return screen
+    sag = item["grid_sag"]
+    memo = cache.get(("raw", id(sag))) if cache is not None else None
+    if memo is not None and memo[3] is sag:
+        return memo[0], memo[1], memo[2]
+    assert sag.ndim == 2, "sag shall be a 2D array"
+    assert sag.shape == (int(item["ny"]), int(item["nx"]))
+    mask = None
+    if isinstance(sag, np.ma.MaskedArray):
+        mask = np.ascontiguousarray(np.ma.getmaskarray(sag), dtype=np.uint8)
+        data = np.ascontiguousarray(sag.filled(0.0), dtype=np.float64)
+    else:
+        data = np.ascontiguousarray(sag, dtype=np.float64)
+    h = hashlib.sha1(data.tobytes())
+    if mask is not None:
+        h.update(mask.tobytes())
+    key = int.from_bytes(h.digest()[:8], "little") or 1
+    if cache is not None:
+        cache[("raw", id(sag))] = (data, mask, key, sag)
+    return data, mask, key
 
 
 def compile_job(job, psd_noise=None, device=None, screen_cache=None):

@@ -28,6 +28,7 @@
 #include "aux_kernels.h"
 #include "device_types.h"
 #include "pass_dispatch.h"
+#include "sag_kernels.h"
 
 using namespace paosb;
 
@@ -1448,6 +1449,353 @@ int paos_wfo_psd(paos_wfo* w, double A, double B, double C, double fknee, double
     return paos_wfo_phase_screen_device(w, screen, wl);
 }
 
+// ---- Grid Sag: device preparation of the map (wfo.py:696-862) ---------------------------------------------------
+namespace {
+
+// Impulse response of scipy.ndimage.fourier_shift along one axis of length n for a complex transform (the reference
+// multiplies fft2(sag) by it and takes ifft2(...).real, wfo.py:768-773): multiplier exp(-2*pi*i*shift*f/n) with f = k for
+// 2k < n, else k - n, hence h[m] = (1/n) * sum_f exp(2*pi*i*f*(m - shift)/n), a Dirichlet kernel in closed form.
+void fourier_shift_kernel(int n, double shift, std::vector<double>& re, std::vector<double>& im) {
+    re.assign(n, 0.0);
+    im.assign(n, 0.0);
+    const long double PI = 3.14159265358979323846264338327950288L;
+    const bool even = (n % 2) == 0;
+    for (int m = 0; m < n; ++m) {
+        const long double d = (long double)m - (long double)shift;  // u/2 = pi*d/n
+        const long double half = PI * d / (long double)n;
+        const long double den = sinl(half);
+        long double mag;
+        if (fabsl(den) < 1e-18L) {
+            mag = (long double)n * cosl(PI * d) / cosl(half);  // limit of sin(n x)/sin(x) at a multiple of pi
+        } else {
+            mag = sinl(PI * d) / den;
+        }
+        // odd n: f runs over -(n-1)/2 .. (n-1)/2 (real kernel); even n: -n/2 .. n/2 - 1, phase factor exp(-i*u/2)
+        long double cr = 1.0L, ci = 0.0L;
+        if (even) {
+            cr = cosl(half);
+            ci = -sinl(half);
+        }
+        re[m] = (double)(mag * cr / (long double)n);
+        im[m] = (double)(mag * ci / (long double)n);
+    }
+}
+
+struct SagBuf {  // a rows x cols device array
+    double* p = nullptr;
+    int rows = 0, cols = 0;
+    size_t count() const { return (size_t)rows * cols; }
+};
+
+struct SagWork {  // temporaries of one preparation, freed on exit
+    std::vector<void*> owned;
+    ~SagWork() {
+        for (void* p : owned) cudaFree(p);
+    }
+    cudaError_t alloc(SagBuf& b, int rows, int cols) {
+        b.rows = rows;
+        b.cols = cols;
+        cudaError_t e = cudaMalloc((void**)&b.p, std::max<size_t>(1, b.count()) * sizeof(double));
+        if (e == cudaSuccess) owned.push_back(b.p);
+        return e;
+    }
+    cudaError_t alloc_raw(void** p, size_t bytes) {
+        cudaError_t e = cudaMalloc(p, std::max<size_t>(1, bytes));
+        if (e == cudaSuccess) owned.push_back(*p);
+        return e;
+    }
+};
+
+#define SAG(expr)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(PAOS_ERR_CUDA, "grid sag: %s failed: %s", #expr, cudaGetErrorString(e__));    \
+    } while (0)
+
+// skimage.transform.resize(order=3) of one map: Gaussian pre-filter per axis when anti-aliasing, B-spline pre-filter and
+// evaluation per axis, clip to the input range (paos_b200/resample.py is the host statement of the same operators)
+int sag_resize(SagWork& wk, SagBuf& a, int out_rows, int out_cols, bool anti_aliasing, cudaStream_t st) {
+    double* lohi;
+    SAG(wk.alloc_raw((void**)&lohi, 2 * sizeof(double)));
+    SAG(sag_minmax(a.p, a.count(), lohi, st));
+    const int out_shape[2] = {out_rows, out_cols};
+    for (int axis = 0; axis < 2; ++axis) {
+        const int n_in = axis == 0 ? a.rows : a.cols, n_out = out_shape[axis];
+        const double sigma = anti_aliasing ? std::max(0.0, ((double)n_in / (double)n_out - 1.0) / 2.0) : 0.0;
+        if (sigma > 1e-15) {
+            const int radius = (int)(4.0 * sigma + 0.5);
+            std::vector<double> w(2 * radius + 1);
+            double sum = 0.0;
+            for (int k = -radius; k <= radius; ++k) sum += (w[k + radius] = std::exp(-0.5 / (sigma * sigma) * (double)k * (double)k));
+            for (double& v : w) v /= sum;
+            double* wd;
+            SAG(wk.alloc_raw((void**)&wd, w.size() * sizeof(double)));
+            SAG(cudaMemcpyAsync(wd, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+            SAG(cudaStreamSynchronize(st));  // w is a stack object
+            SagBuf out;
+            SAG(wk.alloc(out, a.rows, a.cols));
+            SAG(sag_fir_mirror(a.p, a.rows, a.cols, axis, wd, radius, out.p, st));
+            a = out;
+        }
+    }
+    for (int axis = 0; axis < 2; ++axis) {
+        SagBuf cf;
+        SAG(wk.alloc(cf, a.rows, a.cols));
+        SAG(cudaMemcpyAsync(cf.p, a.p, a.count() * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        SAG(sag_bspline_prefilter(cf.p, cf.rows, cf.cols, axis, st));
+        SagBuf out;
+        SAG(wk.alloc(out, axis == 0 ? out_shape[0] : a.rows, axis == 1 ? out_shape[1] : a.cols));
+        SAG(sag_bspline_interp(cf.p, cf.rows, cf.cols, axis, out_shape[axis], out.p, st));
+        a = out;
+    }
+    SAG(sag_clip(a.p, a.count(), lohi, st));
+    return PAOS_OK;
+}
+
+int sag_rescale(SagWork& wk, SagBuf& a, double scale_y, double scale_x, bool anti_aliasing, cudaStream_t st) {
+    const int out_rows = (int)std::max(std::nearbyint(scale_y * (double)a.rows), 1.0);
+    const int out_cols = (int)std::max(std::nearbyint(scale_x * (double)a.cols), 1.0);
+    return sag_resize(wk, a, out_rows, out_cols, anti_aliasing, st);
+}
+
+int sag_shift(SagWork& wk, SagBuf& a, double shift0, double shift1, cudaStream_t st) {
+    std::vector<double> re0, im0, re1, im1;
+    fourier_shift_kernel(a.rows, shift0, re0, im0);
+    fourier_shift_kernel(a.cols, shift1, re1, im1);
+    double *d_re0, *d_im0, *d_re1, *d_im1;
+    SAG(wk.alloc_raw((void**)&d_re0, re0.size() * sizeof(double)));
+    SAG(wk.alloc_raw((void**)&d_im0, im0.size() * sizeof(double)));
+    SAG(wk.alloc_raw((void**)&d_re1, re1.size() * sizeof(double)));
+    SAG(wk.alloc_raw((void**)&d_im1, im1.size() * sizeof(double)));
+    SAG(cudaMemcpyAsync(d_re0, re0.data(), re0.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    SAG(cudaMemcpyAsync(d_im0, im0.data(), im0.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    SAG(cudaMemcpyAsync(d_re1, re1.data(), re1.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    SAG(cudaMemcpyAsync(d_im1, im1.data(), im1.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    SAG(cudaStreamSynchronize(st));
+    // Re[(h0 (*)_0)(h1 (*)_1) a] = Re h0 (*) Re h1 (*) a  -  Im h0 (*) Im h1 (*) a
+    SagBuf t, out;
+    SAG(wk.alloc(t, a.rows, a.cols));
+    SAG(wk.alloc(out, a.rows, a.cols));
+    SAG(sag_conv_circ(a.p, a.rows, a.cols, 1, d_re1, 1.0, 0, t.p, st));
+    SAG(sag_conv_circ(t.p, a.rows, a.cols, 0, d_re0, 1.0, 0, out.p, st));
+    bool any_im = false;
+    for (double v : im0) any_im = any_im || v != 0.0;
+    bool any_im1 = false;
+    for (double v : im1) any_im1 = any_im1 || v != 0.0;
+    if (any_im && any_im1) {
+        SAG(sag_conv_circ(a.p, a.rows, a.cols, 1, d_im1, 1.0, 0, t.p, st));
+        SAG(sag_conv_circ(t.p, a.rows, a.cols, 0, d_im0, -1.0, 1, out.p, st));
+    }
+    a = out;
+    return PAOS_OK;
+}
+
+int sag_fit(SagWork& wk, SagBuf& a, int diff, int axis, double fill, cudaStream_t st) {
+    if (diff == 0) return PAOS_OK;
+    int rows = a.rows, cols = a.cols, row_off = 0, col_off = 0;
+    int& n = axis == 0 ? rows : cols;
+    int& off = axis == 0 ? row_off : col_off;
+    if (diff < 0) {
+        const int before = (-diff) / 2;
+        off = -before;
+        n = n - diff;
+    } else {
+        const int lo = diff / 2;
+        off = lo;
+        n = std::max(0, n - diff);
+    }
+    SagBuf out;
+    SAG(wk.alloc(out, rows, cols));
+    SAG(sag_padcrop(a.p, a.rows, a.cols, row_off, col_off, fill, rows, cols, out.p, st));
+    a = out;
+    return PAOS_OK;
+}
+
+}  // namespace
+
+extern "C" int paos_fourier_shift_kernel(int n, double shift, double* re_out, double* im_out) {
+    if (n < 1 || !re_out || !im_out) return fail(PAOS_ERR_ARG, "bad argument");
+    std::vector<double> re, im;
+    fourier_shift_kernel(n, shift, re, im);
+    std::memcpy(re_out, re.data(), re.size() * sizeof(double));
+    std::memcpy(im_out, im.data(), im.size() * sizeof(double));
+    return PAOS_OK;
+}
+
+// prepare the n x n screen (and, if asked, its mask) of a raw map on the handle's stream; blocks until it is ready
+static int prepare_grid_sag(paos_wfo* w, const double* host_sag, const unsigned char* host_mask, int nx, int ny, double delx, double dely,
+                            double xdec, double ydec, double dx, double dy, double* screen, unsigned char* dmask) {
+    int rc;
+    const int n = w->n;
+    cudaStream_t st = w->stream;
+    // sizes first (wfo.py:776-814), so that an absurd pitch is refused before anything is allocated
+    long cols = nx, rows = ny;
+    int width_diff = (int)std::floor(((double)cols * delx - (double)n * dx) / delx);
+    int height_diff = (int)std::floor(((double)rows * dely - (double)n * dy) / dely);
+    {
+        const double wide = (double)std::max<long>(cols - 2L * std::min(width_diff, 0), 1);
+        const double tall = (double)std::max<long>(rows - 2L * std::min(height_diff, 0), 1);
+        if (wide * tall > (double)(1L << 28))
+            return fail(PAOS_ERR_ARG, "grid_sag: padding the %d x %d map (pitch %g x %g m) to the WFO extent (%g x %g m) needs more than 2^28 samples",
+                        ny, nx, delx, dely, n * dx, n * dy);
+    }
+    SagWork wk;
+    const size_t total = (size_t)nx * ny;
+    double* raw;
+    unsigned char* given = nullptr;
+    SAG(wk.alloc_raw((void**)&raw, total * sizeof(double)));
+    SAG(cudaMemcpyAsync(raw, host_sag, total * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (host_mask) {
+        SAG(wk.alloc_raw((void**)&given, total));
+        SAG(cudaMemcpyAsync(given, host_mask, total, cudaMemcpyHostToDevice, st));
+    }
+    SagBuf sag, mask;
+    SAG(wk.alloc(sag, ny, nx));
+    SAG(wk.alloc(mask, ny, nx));
+    SAG(sag_split(raw, given, total, sag.p, mask.p, st));
+    if (xdec != 0.0 || ydec != 0.0) {  // step 1 (wfo.py:768-773): fourier_shift(..., shift=(-xdec, -ydec)) acts on (axis 0, axis 1)
+        if ((rc = sag_shift(wk, sag, -xdec, -ydec, st)) || (rc = sag_shift(wk, mask, -xdec, -ydec, st))) return rc;
+    }
+    // step 2: pad or crop to the extent of the WFO grid; an odd difference is made even by sampling twice as finely
+    auto is_odd = [](int v) { return ((v % 2) + 2) % 2 == 1; };
+    double sx = 1.0, sy = 1.0;
+    if (is_odd(width_diff)) {
+        sx = 2.0;
+        delx /= 2.0;
+        width_diff *= 2;
+    }
+    if (is_odd(height_diff)) {
+        sy = 2.0;
+        dely /= 2.0;
+        height_diff *= 2;
+    }
+    if (sx != 1.0 || sy != 1.0) {
+        const bool aa = sx < 1.0 || sy < 1.0;
+        if ((rc = sag_rescale(wk, sag, sy, sx, aa, st)) || (rc = sag_rescale(wk, mask, sy, sx, aa, st))) return rc;
+    }
+    if ((rc = sag_fit(wk, sag, width_diff, 1, 0.0, st)) || (rc = sag_fit(wk, mask, width_diff, 1, 1.0, st))) return rc;
+    if ((rc = sag_fit(wk, sag, height_diff, 0, 0.0, st)) || (rc = sag_fit(wk, mask, height_diff, 0, 1.0, st))) return rc;
+    if (sag.rows < 1 || sag.cols < 1) return fail(PAOS_ERR_ARG, "grid_sag: the map does not overlap the WFO grid");
+    // step 3: bring the map to the WFO pixel pitch; step 4: force the exact grid shape (can be one pixel off)
+    sx = delx / dx;
+    sy = dely / dy;
+    if (sx != 1.0 || sy != 1.0) {
+        const bool aa = sx < 1.0 || sy < 1.0;
+        if ((rc = sag_rescale(wk, sag, sy, sx, aa, st)) || (rc = sag_rescale(wk, mask, sy, sx, aa, st))) return rc;
+    }
+    if (sag.rows != n || sag.cols != n) {
+        const bool aa = (double)n / sag.cols < 1.0 || (double)n / sag.rows < 1.0;
+        if ((rc = sag_resize(wk, sag, n, n, aa, st)) || (rc = sag_resize(wk, mask, n, n, aa, st))) return rc;
+    }
+    SAG(sag_finish(sag.p, mask.p, (size_t)n * n, screen, dmask, st));
+    w->stats.kernel_launches += 8;
+    SAG(cudaStreamSynchronize(st));  // the temporaries are freed when `wk` goes out of scope
+    return PAOS_OK;
+}
+
+static int check_grid_sag_args(paos_wfo* w, const double* host_sag, int nx, int ny, double delx, double dely, double xdec, double ydec,
+                               double dx, double dy, double wl) {
+    if (!w || !host_sag) return fail(PAOS_ERR_ARG, "null argument");
+    if (nx < 1 || ny < 1 || !(delx > 0) || !(dely > 0) || !(dx > 0) || !(dy > 0) || !(wl > 0) || !std::isfinite(xdec) || !std::isfinite(ydec))
+        return fail(PAOS_ERR_ARG, "bad grid-sag geometry");
+    return PAOS_OK;
+}
+
+extern "C" int paos_wfo_grid_sag(paos_wfo* w, const double* host_sag, const unsigned char* host_mask, int nx, int ny, double delx,
+                                 double dely, double xdec, double ydec, double dx, double dy, double wl, double* screen_host_out,
+                                 unsigned char* mask_host_out) {
+    int rc = check_grid_sag_args(w, host_sag, nx, ny, delx, dely, xdec, ydec, dx, dy, wl);
+    if (rc) return rc;
+    if (w->recording && (screen_host_out || mask_host_out)) return fail(PAOS_ERR_STATE, "a recording handle cannot return the screen to the host");
+    if ((rc = set_device(w))) return rc;
+    const size_t nn = (size_t)w->n * w->n;
+    double* screen;
+    if ((rc = get_screen(w, &screen))) return rc;
+    DevBuf dmask;
+    if (mask_host_out) CU(dmask.alloc(nn));
+    if ((rc = prepare_grid_sag(w, host_sag, host_mask, nx, ny, delx, dely, xdec, ydec, dx, dy, screen, dmask.as<unsigned char>()))) return rc;
+    if (screen_host_out) CU(cudaMemcpyAsync(screen_host_out, screen, nn * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+    if (mask_host_out) CU(cudaMemcpyAsync(mask_host_out, dmask.p, nn, cudaMemcpyDeviceToHost, w->stream));
+    if (screen_host_out || mask_host_out) CU(cudaStreamSynchronize(w->stream));
+    return paos_wfo_phase_screen_device(w, screen, wl);
+}
+
+// Prepared screens shared between the jobs of a sweep (one map, hundreds of wavelengths): keyed by the caller's content
+// key and every number the preparation depends on.  Entries live until paos_grid_sag_cache_clear (at most 32 are kept).
+namespace {
+struct SagCacheEntry {
+    double* screen = nullptr;
+    cudaEvent_t ready = nullptr;
+};
+std::mutex g_sag_mutex;
+std::map<std::string, SagCacheEntry> g_sag_cache;
+}  // namespace
+
+extern "C" int paos_grid_sag_cache_clear(void) {
+    std::lock_guard<std::mutex> lock(g_sag_mutex);
+    for (auto& kv : g_sag_cache) {
+        if (kv.second.ready) cudaEventDestroy(kv.second.ready);
+        if (kv.second.screen) cudaFree(kv.second.screen);
+    }
+    g_sag_cache.clear();
+    cudaGetLastError();
+    return PAOS_OK;
+}
+
+// chain runner: a Grid Sag surface at whatever pitch the beam has there
+static int chain_grid_sag(paos_wfo* w, const paos_surface& s, double dx, double dy, double wl) {
+    int rc = check_grid_sag_args(w, s.sag, s.sag_nx, s.sag_ny, s.sag_delx, s.sag_dely, s.sag_xdec, s.sag_ydec, dx, dy, wl);
+    if (rc) return rc;
+    if ((rc = set_device(w))) return rc;
+    if (s.sag_key == 0) {
+        double* screen;
+        if ((rc = get_screen(w, &screen))) return rc;
+        if ((rc = prepare_grid_sag(w, s.sag, s.sag_mask, s.sag_nx, s.sag_ny, s.sag_delx, s.sag_dely, s.sag_xdec, s.sag_ydec, dx, dy, screen, nullptr)))
+            return rc;
+        return paos_wfo_phase_screen_device(w, screen, wl);
+    }
+    char key[512];
+    snprintf(key, sizeof key, "%d|%llu|%d|%d|%d|%a|%a|%a|%a|%a|%a", w->device, (unsigned long long)s.sag_key, w->n, s.sag_nx, s.sag_ny,
+             s.sag_delx, s.sag_dely, s.sag_xdec, s.sag_ydec, dx, dy);
+    SagCacheEntry entry;
+    {
+        std::lock_guard<std::mutex> lock(g_sag_mutex);
+        auto it = g_sag_cache.find(key);
+        if (it != g_sag_cache.end()) entry = it->second;
+    }
+    if (!entry.screen) {
+        double* screen = nullptr;
+        CU(cudaMalloc((void**)&screen, (size_t)w->n * w->n * sizeof(double)));
+        rc = prepare_grid_sag(w, s.sag, s.sag_mask, s.sag_nx, s.sag_ny, s.sag_delx, s.sag_dely, s.sag_xdec, s.sag_ydec, dx, dy, screen, nullptr);
+        if (rc) {
+            cudaFree(screen);
+            return rc;
+        }
+        entry.screen = screen;
+        CU(cudaEventCreateWithFlags(&entry.ready, cudaEventDisableTiming));
+        CU(cudaEventRecord(entry.ready, w->stream));
+        std::lock_guard<std::mutex> lock(g_sag_mutex);
+        auto it = g_sag_cache.find(key);
+        if (it != g_sag_cache.end()) {  // another thread prepared the same map meanwhile: keep one
+            cudaEventDestroy(entry.ready);
+            cudaFree(entry.screen);
+            entry = it->second;
+        } else if (g_sag_cache.size() < 32) {
+            g_sag_cache[key] = entry;
+        } else {
+            // cache full: this one screen is kept alive for the life of the process rather than freed under a queued pass
+        }
+    }
+    cudaEvent_t ready = entry.ready;
+    rc = do_fn(w, 0, [=](cudaStream_t st) {
+        cudaError_t e = cudaStreamWaitEvent(st, ready, 0);
+        return e == cudaSuccess ? PAOS_OK : fail(PAOS_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
+    });
+    if (rc) return rc;
+    return paos_wfo_phase_screen_device(w, entry.screen, wl);
+}
+
 // ---- propagators ---------------------------------------------------------------------------------
 static void push_sign(paos_wfo* w) {
     Op op{};
@@ -1880,6 +2228,8 @@ extern "C" int paos_chain_run(paos_wfo* w, double pupil_diameter, double wavelen
                             i, s.screen_dx, s.screen_dy, b.dx, b.dy);
             rc = s.screen_on_device ? paos_wfo_phase_screen_device(w, s.screen, b.wl) : paos_wfo_phase_screen(w, s.screen, b.wl);
             if (rc) return rc;
+        } else if (s.type == PAOS_SURF_GRIDSAG) {
+            if ((rc = chain_grid_sag(w, s, b.dx, b.dy, b.wl))) return rc;
         } else if (s.type == PAOS_SURF_PSD) {
             const double f_nyq = 0.5 * std::sqrt(1.0 / sq(b.dx) + 1.0 / sq(b.dy));
             if (!(s.psd[5] <= f_nyq)) return fail(PAOS_ERR_ARG, "fmax must be less than or equal to f_Nyq (%g)", f_nyq);

@@ -422,15 +422,26 @@ class WFO:
         return np.ma.MaskedArray(wfe, mask=outside, fill_value=0.0)
 
     def grid_sag(self, sag, nx, ny, delx, dely, xdec=0.0, ydec=0.0):
-        """Grid-sag phase screen (``wfo.py:656-871``).  The map is masked, recentred and padded / cropped on the host
-        (``paos_b200/sag.py``, input preparation as in the reference); the phase multiply runs in the fused passes.
-        Maps off the WFO pitch are resampled by ``paos_b200/resample.py``, a restatement of scikit-image 0.24's
-        ``rescale`` / ``resize`` that is not pinned against the library itself (absent from this image)."""
-        from .sag import prepare_sag
-
-        screen, mask = prepare_sag(sag, int(nx), int(ny), delx, dely, xdec, ydec, self._n, self._dx, self._dy)
-        check(lib.paos_wfo_phase_screen(self._handle, screen.ctypes.data_as(C.c_void_p), float(self._wl)))
-        return np.ma.MaskedArray(np.where(mask, 0.0, screen), mask=mask)
+        """Grid-sag phase screen (``wfo.py:656-871``).  The map is masked, recentred (Fourier shift), padded / cropped to the
+        extent of the grid and resampled to the wavefront's pitch (cubic B-splines, Gaussian anti-aliasing) on the device
+        (``paos_wfo_grid_sag``, ``csrc/sag_kernels.cu``); the phase multiply runs in the fused passes.  The resampling
+        restates scikit-image 0.24's ``rescale`` / ``resize`` and is not pinned against the library itself (absent from this
+        image).  Returns the resampled map as a masked array like the reference."""
+        assert sag.ndim == 2, "sag shall be a 2D array"
+        assert sag.shape == (int(ny), int(nx))
+        mask_in = None
+        if isinstance(sag, np.ma.MaskedArray):
+            mask_in = np.ascontiguousarray(np.ma.getmaskarray(sag), dtype=np.uint8)
+            data = np.ascontiguousarray(sag.filled(0.0), dtype=np.float64)
+        else:
+            data = np.ascontiguousarray(sag, dtype=np.float64)
+        screen = np.empty((self._n, self._n), dtype=np.float64)
+        mask = np.empty((self._n, self._n), dtype=np.uint8)
+        check(lib.paos_wfo_grid_sag(
+            self._handle, data.ctypes.data_as(C.c_void_p), mask_in.ctypes.data_as(C.c_void_p) if mask_in is not None else None,
+            int(nx), int(ny), float(delx), float(dely), float(xdec), float(ydec), float(self._dx), float(self._dy), float(self._wl),
+            screen.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p)))
+        return np.ma.MaskedArray(screen, mask=mask.astype(bool))
 
     def psd(self, A=10.0, B=0.0, C=0.0, fknee=1.0, fmin=None, fmax=None, SR=0.0, units=None, noise=None,
             seed=None, return_wfe=True):

@@ -123,3 +123,83 @@ def test_grid_sag_chain_4096_against_oracle(tmp_path):
     for num in ref:
         assert relerr(got[num]["amplitude"], ref[num]["amplitude"]) <= TOL["complex128"], num
         assert got[num]["dx"] == ref[num]["dx"]
+
+
+def _oracle_pool_amplitudes(jobs, noise=None):
+    """IMAGE_PLANE amplitudes of `jobs` from the numpy oracle, one process per job (a 2048^2 chain is ~40 s of numpy)."""
+    import multiprocessing as mp
+
+    with mp.get_context("spawn").Pool(min(len(jobs), 8)) as pool:
+        return pool.map(_oracle_one, [(j, noise) for j in jobs])
+
+
+def _oracle_one(args):
+    from oracle import paos_np
+    from paos_b200 import configs
+
+    job, noise = args
+    kw = {}
+    if noise:
+        kw = {"noise_for": configs.psd_noise_from_seed(job["psd_seed"]), "unit_to_m": lambda u: u.to(type(u)("m"))}
+    res = paos_np.run(job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"], job["opt_chain"], **kw)
+    return res[max(res)]["amplitude"]
+
+
+def _strip(job):
+    return {k: v for k, v in job.items() if not k.startswith("_")}
+
+
+def test_headline_sweep_2048_other_route_and_off_axis_fields():
+    """The jobs the scaling run gives ranks 1-7 (field point r: ut = tan(0.01 r deg)) and the wavelengths whose pilot beam
+    takes the other propagator route (35 instead of 39 FFT2), at the full 2048^2, in ONE batched sweep, against the oracle."""
+    from paos_b200 import configs
+    from paos_b200.sweep import Sweep
+
+    base = configs.airs_ch0(grid=2048, n_wl=256)
+    probe = Sweep(2048, slots=1, what="psf", batch=1)
+    counts = []
+    for j in base:
+        f0 = probe.stats()["fft2_recorded"]
+        probe.run([j])
+        counts.append(probe.stats()["fft2_recorded"] - f0)
+    del probe
+    common = max(set(counts), key=counts.count)
+    odd = [i for i, c in enumerate(counts) if c != common]
+    assert 1 <= len(odd) <= 8 and common == 39
+    jobs = [dict(base[i]) for i in odd[:2]]
+    for r, i in ((3, 20), (7, 250), (5, odd[-1])):
+        j = dict(base[i])
+        j["field"] = {"us": j["field"]["us"], "ut": j["field"]["ut"] + float(np.tan(np.deg2rad(0.01 * r)))}
+        jobs.append(j)
+    refs = _oracle_pool_amplitudes([_strip(j) for j in jobs])
+    sw = Sweep(2048, slots=1, what="amplitude", batch=8)
+    out, meta = sw.run(jobs)
+    out = out.cpu().numpy()
+    for k, ref in enumerate(refs):
+        assert relerr(out[k], ref) <= TOL["complex128"], (k, jobs[k]["tag"])
+
+
+def test_fgs1_realization_2048_against_oracle():
+    """BASELINE config 3 at 2048^2: one Monte-Carlo WFE realization (36 Zernike terms from the realization table)."""
+    from paos_b200 import configs
+    from paos_b200.sweep import Sweep
+
+    jobs = configs.fgs1_montecarlo(grid=2048, realizations=[17])
+    ref = _oracle_pool_amplitudes([_strip(jobs[0])])[0]
+    out, _ = Sweep(2048, slots=1, what="amplitude", batch=2).run(jobs)
+    assert relerr(out[0].cpu().numpy(), ref) <= TOL["complex128"]
+
+
+def test_ta_ground_psd_every_field_against_oracle():
+    """BASELINE config 4: one (field, wavelength) job per field point of the 3 x 3 grid, PSD noise injected."""
+    from paos_b200 import configs
+    from paos_b200.sweep import Sweep
+
+    allj = configs.ta_ground_psd(grid=1024, n_wl=3)
+    jobs = [allj[f * 3 + (f % 3)] for f in range(9)]  # field f, wavelength f % 3
+    refs = _oracle_pool_amplitudes([_strip(j) for j in jobs], noise=True)
+    noise = lambda job: configs.psd_noise_from_seed(job["psd_seed"])  # noqa: E731
+    out, _ = Sweep(1024, slots=1, what="amplitude", batch=4).run(jobs, psd_noise=noise)
+    out = out.cpu().numpy()
+    for k, ref in enumerate(refs):
+        assert relerr(out[k], ref) <= TOL["complex128"], jobs[k]["tag"]

@@ -191,10 +191,10 @@ def test_gather_stack_world_size_2_gloo(tmp_path):
     (51, 77, (1.3, 0.8), -0.7, 2.2), (838 // 4, 1158 // 4, (0.37, 0.37), 0.0, 0.0),
 ])
 def test_grid_sag_resampling_matches_oracle(ny, nx, pitch, xdec, ydec):
-    """paos_b200.sag.prepare_sag (own separable cubic resampler) against the oracle's grid_sag (scipy.ndimage restatement
+    """oracle.sag_host.prepare_sag (the separable operators the device kernels run, stated on the host) against the oracle's grid_sag (scipy.ndimage restatement
     of the skimage calls, wfo.py:696-862): same mask, same screen to rounding."""
     from oracle import paos_np
-    from paos_b200.sag import prepare_sag
+    from oracle.sag_host import prepare_sag
 
     n = 64
     rng = np.random.default_rng(5)
@@ -212,7 +212,7 @@ def test_grid_sag_resampling_matches_oracle(ny, nx, pitch, xdec, ydec):
 def test_resampler_known_answers():
     """Properties of the cubic resampler that hold whatever library restates it: constants and linear ramps inside the
     clip range are reproduced, identity scale returns the input, shapes follow round(scale * shape)."""
-    from paos_b200 import resample
+    from oracle import separable_resample as resample
 
     a = np.full((9, 14), 2.5)
     assert np.allclose(resample.rescale(a, (1.7, 0.6), True), 2.5, atol=1e-14)
@@ -245,29 +245,34 @@ def test_oracle_encircled_energy_of_a_gaussian():
     assert np.all(np.diff(ee) >= 0)
 
 
-def test_native_compile_refuses_grid_sag_behind_a_propagation(tmp_path):
-    """The native runner prepares a grid-sag screen for the INIT pitch; a Grid Sag surface behind a propagation has to
-    go through the Python driver (chain.py raises NotImplementedError, Sweep catches it)."""
+def test_native_compile_takes_grid_sag_anywhere_in_the_chain(tmp_path):
+    """The native runner carries the raw map and lets the library resample it at the pitch of the surface (wfo.py:848-862),
+    so a Grid Sag surface behind a propagation compiles like one at the INIT pitch; maps that are the same object share one
+    content key (one prepared screen per sweep)."""
     import copy
 
     from paos_b200 import chain as chain_mod
     from paos_b200 import configs
 
     job = configs.grid_sag(grid=64, wavelengths=(3.0,), workdir=str(tmp_path))[0]
-    chain_mod.compile_job(job)  # as shipped: the Grid Sag surface sits right behind the stop, at the INIT pitch
-    assert job["_compiled"].array[1].screen_dx == job["pupil_diameter"] * job["zoom"] / 64
-    late = copy.deepcopy(job["opt_chain"][3])
+    cache = {}
+    cc = chain_mod.compile_job(job, screen_cache=cache)
+    rec = cc.array[1]
+    assert rec.type == chain_mod.SURF_GRIDSAG and rec.sag_nx == 64 and rec.sag_ny == 64 and rec.sag_key != 0
+    assert rec.sag_delx == job["pupil_diameter"] * job["zoom"] / 64
+    late = copy.copy(job["opt_chain"][3])
     late.update(num=5.5, name="Sag2")
     moved = {k: v for k, v in job["opt_chain"].items()}
     moved[5.5] = late
     job2 = dict(job, opt_chain=dict(sorted(moved.items())))
     job2.pop("_compiled", None)
-    with pytest.raises(NotImplementedError):
-        chain_mod.compile_job(job2)
+    cc2 = chain_mod.compile_job(job2, screen_cache=cache)
+    keys = [r.sag_key for r in cc2.array[: cc2.count] if r.type == chain_mod.SURF_GRIDSAG]
+    assert len(keys) == 2 and keys[0] == keys[1] == rec.sag_key
 
 
 def test_grid_sag_refuses_absurd_padding():
-    from paos_b200.sag import prepare_sag
+    from oracle.sag_host import prepare_sag
 
     with pytest.raises(ValueError):
         prepare_sag(np.ones((90, 70)), 70, 90, 6e-5, 6e-5, 0.0, 0.0, 256, 0.0172, 0.0172)
@@ -275,7 +280,8 @@ def test_grid_sag_refuses_absurd_padding():
 
 def test_pipeline_chain_setup_and_refusals():
     """paos_b200.pipeline's option handling (pipeline.py:88-129): light_output keeps only IMAGE_PLANE, the -wfe option
-    overrides Z1 with column c + 4 of the realization table; save / plot requests are refused, not dropped."""
+    overrides Z1 with column c + 4 of the realization table; the default save=True needs an output name (as in the
+    reference, which indexes passvalue['output']), plot requests are refused, not dropped."""
     import paos_b200
     from paos_b200 import configs
 
@@ -291,7 +297,7 @@ def test_pipeline_chain_setup_and_refusals():
             assert it["name"] != "Z1"
     want = np.append(np.zeros(3), configs.wfe_table()[:, 3 + 7] * 1e-9)
     assert np.array_equal(np.append(np.zeros(3), pl.read_wfe_column(csv, "7")), want) and len(want) == 36
-    with pytest.raises(NotImplementedError):
-        paos_b200.pipeline({"conf": conf})  # save defaults to True, as in the reference
+    with pytest.raises(KeyError):
+        paos_b200.pipeline({"conf": conf})  # save defaults to True, as in the reference: it needs passvalue['output']
     with pytest.raises(NotImplementedError):
         paos_b200.pipeline({"conf": conf, "save": False, "plot": True})

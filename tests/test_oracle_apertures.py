@@ -69,3 +69,99 @@ def test_clipped_by_grid():
     m = ap.elliptical_mask((32, 32), 2.0, 30.5, 6.0, 5.0)
     full = ap.elliptical_mask((96, 96), 34.0, 62.5, 6.0, 5.0)
     assert np.array_equal(m, full[32:64, 32:64])
+
+
+# ---- the 32 x 32 sub-pixel rule in exact rational arithmetic ---------------------------------
+# photutils (1.11.0 in the reference's poetry.lock; source absent here) evaluates a rectangle on its bounding box:
+# edges  xmin = ixmin - 0.5 - xc, xmax = ixmax - 0.5 - xc, pixel width dx = (xmax - xmin)/nx, pixel i spans
+# [xmin + i*dx, xmin + (i+1)*dx], sub-pixel step d = dx/32, x = pxmin - d/2; x += d; inside iff |x| < w/2 (strict).
+# The oracle (and the device table builder, aux_kernels.cu: subpixel_count) form pxmin = (i - 0.5) - xc directly.  Both are
+# roundings of the same rational rule: sub-pixel centre (i - 1/2) + (2s + 1)/64 - xc strictly inside (-w/2, w/2).
+def _exact_counts(n, c, full):
+    from fractions import Fraction
+
+    c, half = Fraction(c), Fraction(full) / 2
+    out = np.zeros(n, dtype=np.int64)
+    lo, hi = int(np.floor(float(c - half))) - 2, int(np.ceil(float(c + half))) + 2
+    for k in range(max(lo, 0), min(hi, n)):
+        out[k] = sum(1 for s in range(32) if abs(Fraction(2 * k - 1, 2) + Fraction(2 * s + 1, 64) - c) < half)
+    return out
+
+
+def _bbox_form_counts(n, c, full):
+    """The published bounding-box form in float arithmetic (restated from the photutils 1.11 algorithm description)."""
+    half = full / 2.0
+    ixmin, ixmax = int(np.floor(c - half + 0.5)), int(np.ceil(c + half + 0.5))
+    nx = ixmax - ixmin
+    xmin, xmax = ixmin - 0.5 - c, ixmax - 0.5 - c
+    dx = (xmax - xmin) / nx
+    out = np.zeros(n, dtype=np.int64)
+    for i in range(nx):
+        k = ixmin + i
+        if not 0 <= k < n:
+            continue
+        pxmin = xmin + i * dx
+        pxmax = pxmin + dx
+        d = (pxmax - pxmin) / 32
+        x = pxmin - 0.5 * d
+        cnt = 0
+        for _ in range(32):
+            x += d
+            if abs(x) < half:
+                cnt += 1
+        out[k] = cnt
+    return out
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096])
+def test_hubble_rectangles_subpixel_rule_is_rounding_free(n):
+    """Config 1 (Hubble_simple.ini: rectangular obscurations 0.0264 m x 2.5 m and 2.5 m x 0.0264 m at the centre, dx =
+    2.4*4/n): the exact rational rule, the oracle's float form and the bounding-box float form give the same counts, at
+    every grid size -- no edge sits within rounding distance of a sub-pixel centre."""
+    from oracle.apertures import _subpixel_counts_1d
+
+    dx = 2.4 * 4 / n
+    c = 0.0 / dx + n / 2
+    for side_m in (0.0264, 2.5):
+        full = side_m / dx
+        exact = _exact_counts(n, c, full)
+        assert np.array_equal(_subpixel_counts_1d(n, c, full), exact)
+        assert np.array_equal(_bbox_form_counts(n, c, full), exact)
+        assert exact.sum() > 0
+
+
+def test_subpixel_rule_when_an_edge_meets_a_subpixel_centre():
+    """Worst case for the restatement: an edge exactly on a sub-pixel centre.  (a) Dyadic geometry (centre on a pixel centre
+    or edge, side an odd multiple of 1/32 px): every quantity is exact in binary floating point, so both float forms equal
+    the rational rule -- the centre on the edge is *outside* (strict inequality).  (b) Non-dyadic centres with the side
+    chosen so that the rational edge falls on a rational sub-pixel centre to within one ulp: the float forms may then
+    disagree with each other by at most ONE sub-pixel in the edge pixel of each side, i.e. 1/32 of that pixel column (mask
+    deviation <= cy/1024 <= 1/32), and by nothing anywhere else."""
+    from oracle.apertures import _subpixel_counts_1d
+
+    n = 128
+    for c in (64.0, 64.5, 63.75):
+        for m in range(1, 200, 2):  # odd multiples of 1/32 px
+            full = m / 32.0
+            exact = _exact_counts(n, c, full)
+            assert np.array_equal(_subpixel_counts_1d(n, c, full), exact), (c, m)
+            assert np.array_equal(_bbox_form_counts(n, c, full), exact), (c, m)
+    rng = np.random.default_rng(7)
+    worst = 0
+    trials = disagreements = 0
+    for _ in range(300):
+        c = 64.0 + rng.uniform(-3, 3)
+        k, s = int(rng.integers(70, 100)), int(rng.integers(0, 32))
+        centre = ((k - 0.5) + (2 * s + 1) / 64.0) - c  # float position of one sub-pixel centre
+        for full in (2.0 * centre, np.nextafter(2.0 * centre, np.inf), np.nextafter(2.0 * centre, -np.inf)):
+            a = _subpixel_counts_1d(n, c, full)
+            b = _bbox_form_counts(n, c, full)
+            e = _exact_counts(n, c, full)
+            trials += 1
+            diff_ab, diff_ae = np.abs(a - b), np.abs(a - e)
+            disagreements += int(diff_ab.any() or diff_ae.any())
+            worst = max(worst, int(diff_ab.max()), int(diff_ae.max()))
+            assert diff_ab.sum() <= 2 and diff_ae.sum() <= 2  # at most one sub-pixel at each of the two edges
+    assert worst <= 1
+    # recorded in DESIGN.md section 6: such coincidences need an edge within one ulp (~1e-14 px) of a sub-pixel centre
+    print(f"adversarial edges: {disagreements}/{trials} cases differ, worst count difference {worst} of 32")
