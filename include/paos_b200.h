@@ -332,6 +332,10 @@ typedef struct paos_stats {
     uint64_t fft2_recorded;     /* FFT2s requested through the API (algorithmic count) */
     uint64_t line_ffts_run;     /* 1-D line-FFT batches executed (2 per FFT2) */
     uint64_t lines_transformed; /* single lines actually transformed (a batch is n lines unless an aperture blanks some) */
+    uint64_t lines_tabled;      /* along-line phase-table multiplies, in lines (tables of a pass x lines it really processes) */
+    uint64_t lines_swept;       /* lines loaded and stored by the passes (one per pass and live line) */
+    uint64_t host_plan_us;      /* host microseconds spent inside paos_chain_run / paos_batch_chain_run: walking the surfaces,
+                                   planning the passes and issuing the launches (booked on the first handle of a batch) */
     double last_flush_ms;       /* device time of the most recent flushed batch (CUDA events), 0 if untimed */
 } paos_stats;
 int paos_wfo_stats(paos_wfo *w, paos_stats *out);

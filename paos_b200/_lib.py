@@ -36,6 +36,9 @@ class PaosStats(C.Structure):
         ("fft2_recorded", C.c_uint64),
         ("line_ffts_run", C.c_uint64),
         ("lines_transformed", C.c_uint64),
+        ("lines_tabled", C.c_uint64),
+        ("lines_swept", C.c_uint64),
+        ("host_plan_us", C.c_uint64),
         ("last_flush_ms", C.c_double),
     ]
 

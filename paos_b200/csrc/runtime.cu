@@ -17,11 +17,13 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <functional>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/paos_b200.h"
@@ -516,6 +518,10 @@ static void account_pass(paos_wfo* w, bool col, const PassParams& P) {
     const int W = tile_width(w->n, w->dtype, col), tiles = w->n / W;
     const int active = std::max(0, std::min(P.tile_hi, tiles - 1) - std::max(P.tile_lo, 0) + 1);
     w->stats.lines_transformed += (uint64_t)P.nfft * (uint64_t)active * (uint64_t)W;
+    int tabs = (P.ctab_in ? 1 : 0) + (P.ctab_out ? 1 : 0);
+    for (int p = 0; p <= P.nfft; ++p) tabs += P.tab[p] != nullptr;
+    w->stats.lines_tabled += (uint64_t)tabs * (uint64_t)active * (uint64_t)W;
+    w->stats.lines_swept += (uint64_t)active * (uint64_t)W;
 }
 
 // one launch of the pass kernel for the same-axis passes Ps[0..nb) of handles that share grid size, precision, device and
@@ -968,18 +974,54 @@ int paos_batch_execute(paos_wfo* const* ws, int nb) {
 int paos_batch_chain_run(paos_wfo* const* ws, int nb, const paos_chain_args* args) {
     if (!ws || !args || nb < 1) return fail(PAOS_ERR_ARG, "null argument");
     if (nb > BMAX) return fail(PAOS_ERR_ARG, "a batch holds at most %d wavefronts", BMAX);
-    for (int b = 0; b < nb; ++b) {
-        int rc = ws[b] ? paos_wfo_begin_record(ws[b]) : fail(PAOS_ERR_ARG, "null handle in the batch");
+    const auto t0 = std::chrono::steady_clock::now();
+    struct Book {  // host time of planning + launching, booked on the first handle
+        paos_wfo* w;
+        std::chrono::steady_clock::time_point t0;
+        ~Book() {
+            if (w) w->stats.host_plan_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        }
+    } book{ws[0], t0};
+    // The chains of a batch are independent until they are executed, so their surfaces are walked and their passes planned
+    // by a few host threads (PAOS_PLAN_THREADS, default 4 for batches of 8 and more): at 512^2 the device needs ~25 us
+    // per PSF and one thread's planning would be the bottleneck.
+    static const int max_threads = [] {
+        const char* e = getenv("PAOS_PLAN_THREADS");
+        const int v = e ? atoi(e) : 4;
+        return v < 1 ? 1 : (v > 16 ? 16 : v);
+    }();
+    for (int b = 0; b < nb; ++b)
+        if (!ws[b]) return fail(PAOS_ERR_ARG, "null handle in the batch");
+    std::vector<int> rcs((size_t)nb, PAOS_OK);
+    std::vector<std::string> msgs((size_t)nb);
+    auto record = [&](int b) {
+        int rc = paos_wfo_begin_record(ws[b]);
         if (!rc) {
             const paos_chain_args& a = args[b];
             rc = paos_chain_run(ws[b], a.pupil_diameter, a.wavelength, a.zoom, a.us, a.ut, a.surfaces, a.n_surfaces, a.snapshots,
                                 a.max_snapshots, a.n_snapshots, a.final_state);
         }
-        if (rc) {
-            abandon_records(ws, nb);
-            return rc;
-        }
+        rcs[(size_t)b] = rc;
+        if (rc) msgs[(size_t)b] = g_last_error;  // thread-local: carry it to the calling thread
+    };
+    const int nthreads = nb >= 8 ? std::min(max_threads, nb) : 1;
+    if (nthreads <= 1) {
+        for (int b = 0; b < nb; ++b) record(b);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthreads; ++t)
+            pool.emplace_back([&, t] {
+                for (int b = t; b < nb; b += nthreads) record(b);
+            });
+        for (int b = 0; b < nb; b += nthreads) record(b);
+        for (std::thread& th : pool) th.join();
     }
+    for (int b = 0; b < nb; ++b)
+        if (rcs[(size_t)b]) {
+            abandon_records(ws, nb);
+            g_last_error = msgs[(size_t)b];
+            return rcs[(size_t)b];
+        }
     return paos_batch_execute(ws, nb);
 }
 
@@ -2185,6 +2227,13 @@ extern "C" int paos_chain_run(paos_wfo* w, double pupil_diameter, double wavelen
                               const paos_surface* surfaces, int n_surfaces, paos_snapshot* snapshots, int max_snapshots,
                               int* n_snapshots, paos_snapshot* final_state) {
     if (!w || (!surfaces && n_surfaces > 0)) return fail(PAOS_ERR_ARG, "null argument");
+    struct Book {  // host time of an unbatched chain (a recording handle is timed by paos_batch_chain_run)
+        paos_wfo* w;
+        std::chrono::steady_clock::time_point t0;
+        ~Book() {
+            if (w) w->stats.host_plan_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        }
+    } book{w->recording ? nullptr : w, std::chrono::steady_clock::now()};
     if (!(zoom > 0) || !(pupil_diameter > 0) || !(wavelength > 0)) return fail(PAOS_ERR_ARG, "zoom, beam diameter and wavelength must be positive");
     int rc = paos_wfo_reset(w);
     if (rc) return rc;

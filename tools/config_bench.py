@@ -60,7 +60,8 @@ def main():
                "fft2_per_psf": (st1["fft2_recorded"] - st0["fft2_recorded"]) / len(jobs),
                "passes_per_psf": (st1["passes_planned"] - st0["passes_planned"]) / len(jobs),
                "pass_launches_per_psf": (st1["pass_launches"] - st0["pass_launches"]) / len(jobs),
-               "launches_per_psf": (st1["kernel_launches"] - st0["kernel_launches"]) / len(jobs)}
+               "launches_per_psf": (st1["kernel_launches"] - st0["kernel_launches"]) / len(jobs),
+               "host_plan_us_per_psf": (st1["host_plan_us"] - st0["host_plan_us"]) / len(jobs)}
         rec["algorithmic_GBps"] = rec["fft2_per_psf"] * 64 * n * n * rec["psf_per_s"] / 1e9 * (1 if args.dtype == "complex128" else 0.5)
         if args.cpu:
             from oracle import paos_np
