@@ -1,10 +1,7 @@
 set -x
 cd $GRAFT_REPO_ROOT
-timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/r02e_pytest.log 2>&1; echo "pytest rc=$?"
-tail -12 gpurun_out/r02e_pytest.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02e_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/r02e_smoke.log
-timeout 900 python tools/config_bench.py --only hubble,airs512,airs1024,fgs1,ta_psd > gpurun_out/r02e_cfg_batched.log 2>&1; echo "cfg rc=$?"; grep -v "^{" gpurun_out/r02e_cfg_batched.log | cut -c1-260
-timeout 900 python tools/config_bench.py --only hubble,airs512,airs1024,fgs1,ta_psd --batch 1 > gpurun_out/r02e_cfg_b1.log 2>&1; echo "cfg1 rc=$?"; grep -v "^{" gpurun_out/r02e_cfg_b1.log | cut -c1-260
-timeout 900 python bench.py > gpurun_out/r02e_bench.json 2> gpurun_out/r02e_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/r02e_bench.err
-python -c "
-import json;d=json.load(open('gpurun_out/r02e_bench.json'));print({k:d[k] for k in ('value','ms_per_step','gpu_launches','parity','cpu_baseline','e2e','e2e_ee','e2e_reduced')}); print(d['roofline'])"
+CMD="python bench.py --n-wl 16 --steps 1 --warmup 1 --no-cpu --slots 1"
+timeout 600 $CMD > gpurun_out/r02_plain.json 2> gpurun_out/r02_plain.err; echo "plain rc=$?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches.csv $CMD > gpurun_out/r02_ncu1.log 2>&1; echo "ncu1 rc=$?"
+timeout 1200 ncu --set full --import-source on --clock-control none -k regex:pass_kernel -s 14 -c 14 -f -o gpurun_out/r02_prof $CMD > gpurun_out/r02_ncu2.log 2>&1; echo "ncu2 rc=$?"
+ls -la gpurun_out | tail -8

@@ -72,6 +72,16 @@ def main():
             paos_np.run(job["pupil_diameter"], job["wavelength"], job["gridsize"], job["zoom"], job["field"], job["opt_chain"],
                         noise_for=noise, unit_to_m=lambda u: u.to(type(u)("m")))
             rec["cpu_oracle_s_per_psf_1core"] = time.perf_counter() - t0
+        # device side alone: CUDA events around every pass launch of one more sweep (they serialise the launches, so this
+        # sweep is not the one timed above)
+        sw.enable_timing(True)
+        sw.timing_totals(reset=True)
+        sw.run(jobs, out=stack)
+        tot = sw.timing_totals(reset=True)
+        sw.enable_timing(False)
+        # launch durations summed over the slots' streams: launches of different slots overlap on the device, so this is the
+        # device work per PSF, not a lower bound of the wall time
+        rec["pass_kernel_us_per_psf"] = 1e3 * tot["ms"] / len(jobs)
         out[name] = rec
         print(name, json.dumps(rec), flush=True)
         del sw, stack
