@@ -281,9 +281,7 @@ def timed_steps(torch, sweep, jobs, stack, host_stack, steps, extra_streams=(), 
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     start.record(cur)
-    for s in sweep.streams:
-        s.wait_event(start)
-    for s in extra_streams:
+    for s in list(sweep.streams) + list(getattr(sweep, "copy_streams", [])) + list(extra_streams):
         s.wait_event(start)
     for _ in range(steps):
         if before is not None:
@@ -291,7 +289,7 @@ def timed_steps(torch, sweep, jobs, stack, host_stack, steps, extra_streams=(), 
         sweep.run(jobs, out=stack, host_out=host_stack, cache_compiled=CACHE_COMPILED, **run_kw)
         if after is not None:
             after()
-    for s in list(sweep.streams) + list(extra_streams):
+    for s in list(sweep.streams) + list(getattr(sweep, "copy_streams", [])) + list(extra_streams):
         e = torch.cuda.Event()
         e.record(s)
         cur.wait_event(e)

@@ -96,6 +96,74 @@ cudaError_t launch_build_tables(const TableBlock& B, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// ---- edge tables of the elliptical masks (device_types.h: EdgeSpec) ---------------------------------------------
+// One warp per line.  The half-warps look at 16 consecutive elements around the left and the right crossing of the line
+// with the ellipse's rim, classify them exactly as the pass kernel will (ellipse_r2), and the lanes that fall into the edge
+// band evaluate the exact overlap in parallel.  Lines whose band is wider than the window (within a pixel or so of the
+// poles) are flagged and left to the pass kernel.
+__global__ void __launch_bounds__(256) build_edge_tables_kernel(const __grid_constant__ EdgeBlock B) {
+    const EdgeSpec& sp = B.spec[blockIdx.y];
+    const GenOp& g = sp.g;
+    const int n = B.n, lane = threadIdx.x & 31, line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (line >= n) return;
+    const bool col = sp.col != 0;
+    const int T = sp.T;
+    const double c_al = col ? g.p1 : g.p0, c_cr = col ? g.p0 : g.p1;
+    const float s_al = col ? (float)g.p3 : (float)g.p2, s_cr = col ? (float)g.p2 : (float)g.p3;
+    const float in5 = (float)g.p5 - 1e-5f, out6 = (float)g.p6 + 1e-5f;
+    const float da = __fmul_rn((float)T, s_al);
+    const float b2 = ellipse_b2(line, c_cr, s_cr);
+    int4* hdr = reinterpret_cast<int4*>(sp.out) + line;
+    double* fac = reinterpret_cast<double*>(reinterpret_cast<char*>(sp.out) + (size_t)n * 16) + (size_t)line * 2 * EDGE_CAP;
+    // geometry of the band along this line, in pixels (double; the windows keep a pixel of slack against the FP32 rounding)
+    const double ro2 = (double)out6 - (double)b2, ri2 = (double)in5 - (double)b2;
+    if (!(ro2 > 0.0)) {  // the whole line is outside the band: no edge pixel
+        if (lane == 0) *hdr = make_int4(0, 0, 0, 0);
+        return;
+    }
+    const double ro = sqrt(ro2) / (double)s_al, ri = ri2 > 0.0 ? sqrt(ri2) / (double)s_al : 0.0;
+    bool flag = (ro - ri) + 3.0 > (double)EDGE_CAP || !(ri2 > 0.0) || 2.0 * ri < 34.0;  // wide band, or the two windows could meet
+    const int side = lane >> 4, k = lane & 15;
+    const int start = side == 0 ? (int)floor(c_al - ro) - 2 : (int)ceil(c_al + ro) + 2 - 15;
+    const int idx = start + k;
+    bool edge = false;
+    if (!flag && idx >= 0 && idx < n) {
+        const float r2 = ellipse_r2(ellipse_a0(idx % T, c_al, s_al), da, idx / T, b2);
+        edge = !(r2 <= in5) && !(r2 >= out6);
+    }
+    const unsigned bits = __ballot_sync(0xffffffffu, edge);
+    const unsigned half[2] = {bits & 0xffffu, bits >> 16};
+    int first[2], len[2];
+    for (int s2 = 0; s2 < 2; ++s2) {
+        first[s2] = half[s2] ? __ffs((int)half[s2]) - 1 : 0;
+        len[s2] = __popc(half[s2]);
+        const unsigned run = half[s2] >> first[s2];
+        // the run must be contiguous, fit the table and stay clear of both ends of the window (else it may continue outside)
+        if (half[s2] && ((run & (run + 1)) != 0 || len[s2] > EDGE_CAP || (half[s2] & 0x8001u))) flag = true;
+    }
+    flag = __any_sync(0xffffffffu, flag);
+    if (flag) {
+        if (lane == 0) *hdr = make_int4(0, 0, 1 << 16, 0);
+        return;
+    }
+    if (edge) {
+        const double f = ellipse_fraction(g, (double)(col ? line : idx), (double)(col ? idx : line));
+        fac[side * EDGE_CAP + (k - first[side])] = g.flag ? 1.0 - f : f;
+    }
+    if (lane == 0) {
+        const int s0 = start + first[0] - 0;  // lane 0 is on side 0: its `start` is the left window's
+        const int right_start = (int)ceil(c_al + ro) + 2 - 15;
+        *hdr = make_int4(s0, right_start + first[1], len[0] | (len[1] << 8), 0);
+    }
+}
+
+cudaError_t launch_build_edge_tables(const EdgeBlock& B, cudaStream_t st) {
+    if (B.nspec < 1) return cudaSuccess;
+    dim3 grid((B.n + 7) / 8, B.nspec);
+    build_edge_tables_kernel<<<grid, 256, 0, st>>>(B);
+    return cudaGetLastError();
+}
+
 // ---- stop: sum |field * pending real factors|^2 (wfo.py:200) ----------------------------------------
 struct Norm2Params {
     const void* src;

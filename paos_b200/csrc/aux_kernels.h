@@ -4,6 +4,7 @@
 
 namespace paosb {
 cudaError_t launch_build_tables(const TableBlock& B, cudaStream_t st);
+cudaError_t launch_build_edge_tables(const EdgeBlock& B, cudaStream_t st);
 // one stop reduction (paos/classes/wfo.py:200): sum |src * masks|^2 -> out_slot = (1/sqrt(sum), sum)
 struct Norm2Item {
     const void* src;  // null: the analytic field of ones

@@ -13,7 +13,7 @@ constexpr int TB_MAX = 64;  // tables built by one launch of the table builder (
 // general elementwise factors (real masks, phase screens, device scalars)
 enum GenKind : int {
     GEN_NONE = 0,
-    GEN_ELLIPSE = 1,    // exact pixel/ellipse overlap (theta = 0): p0=xc p1=yc p2=1/a p3=1/b p4=a*b
+    GEN_ELLIPSE = 1,    // exact pixel/ellipse overlap (theta = 0): p0=xc p1=yc p2=1/a p3=1/b p4=a*b; ptr0 = edge table or null
     GEN_RECT = 2,       // 32x32 sub-pixel rectangle: ptr0 = x counts, ptr1 = y counts (double[N])
     GEN_SCREEN = 3,     // exp(i*(2*pi*w)/wl): ptr0 = w (double[N*N]), p0 = wl
     GEN_SCALE_DEV = 4,  // multiply by *ptr0 (double in device memory)
@@ -31,6 +31,15 @@ struct GenOp {
     const void* ptr0;
     const void* ptr1;
 };
+
+// Edge table of one elliptical mask on one pass (built by build_edge_tables_kernel, read by the pass kernel).  Along a line
+// the pixels that are neither certainly inside nor certainly outside the ellipse form at most two short runs, where the
+// line crosses the rim; their exact overlap fractions are evaluated once, one lane per pixel, instead of by a lane or two
+// of the warp that meets them in the pass (a ~400-instruction dependent FP64 chain on the critical path of the whole line).
+//   header[line] = {start0, start1, len0 | len1 << 8 | flag << 16, 0};  factor[(line * 2 + side) * EDGE_CAP + k]
+// flag = 1: this line's runs do not fit (lines within a pixel or so of the ellipse's poles): the pass kernel computes them.
+constexpr int EDGE_CAP = 12;
+__host__ __device__ constexpr size_t edge_table_bytes(int n) { return (size_t)n * 16 + (size_t)n * 2 * EDGE_CAP * sizeof(double); }
 
 struct PassParams {
     const void* src;  // null = field of ones (never materialised)
@@ -95,6 +104,20 @@ struct TableBlock {
     int dtype;  // 0: complex128 tables, 1: complex64 tables (count tables are always double)
     int pad;
     TableSpec spec[TB_MAX];
+};
+
+// one edge table to build: the mask, the axis of the pass that applies it and the threads per line of that pass
+struct EdgeSpec {
+    GenOp g;
+    void* out;
+    int col;  // 1: lines are columns (line = ix, along = iy)
+    int T;    // threads per line of the pass kernel: element idx = t + j * T, classified as the kernel does
+};
+constexpr int EB_MAX = 32;
+struct EdgeBlock {
+    int n;
+    int nspec;
+    EdgeSpec spec[EB_MAX];
 };
 
 constexpr int ZERN_MAX = 64;

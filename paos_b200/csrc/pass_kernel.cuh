@@ -82,6 +82,20 @@ __device__ __forceinline__ double ellipse_fraction(const GenOp& g, double ix, do
     return fmin(fmax(f, 0.0), 1.0);
 }
 
+// FP32 classification of the element idx = t + j*T of a line against an elliptical mask, shared by the pass kernel and the
+// builder of the edge tables (explicit fused operations: both must round identically).  Returns r^2 in the frame where the
+// ellipse is the unit circle; a0 = (along-coordinate of element t minus the centre) * scale, da = T * scale, b2 = (cross
+// coordinate of the line minus the centre)^2 * scale^2.
+__device__ __forceinline__ float ellipse_a0(int t, double c_along, float s_along) { return __fmul_rn((float)((double)t - c_along), s_along); }
+__device__ __forceinline__ float ellipse_b2(int line, double c_cross, float s_cross) {
+    const float bq = __fmul_rn((float)((double)line - c_cross), s_cross);
+    return __fmul_rn(bq, bq);
+}
+__device__ __forceinline__ float ellipse_r2(float a0, float da, int j, float b2) {
+    const float aq = __fmaf_rn((float)j, da, a0);
+    return __fmaf_rn(aq, aq, b2);
+}
+
 // PSD amplitude filter sqrt(psd2d)*sqrt(N*N), zero outside [fmin, fmax] (psd.py:118-129, wfo.py:913-918).
 // p0=A p1=B p2=C p3=fknee p4=fmin p5=fmax p6=valx p7=valy p8=N ; frequencies in unshifted (fftfreq) order
 static __device__ __noinline__ double psd_filter(const GenOp& g, int ix, int iy) {
@@ -374,36 +388,55 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
                 if (g.kind == GEN_ELLIPSE) {
                     // Interior / exterior pixels are classified in FP32 (its pipe is idle next to the FP64 butterflies):
                     // p5, p6 = squared radii, in the frame where the ellipse is the unit circle, inside / outside which
-                    // a whole pixel is certainly inside / outside; the 1e-5 margins cover the float rounding.  Only
-                    // pixels in the thin band between them take the exact (double) routine.
-                    // The centre is subtracted in double (two FP64 instructions per thread and mask): (float)centre alone
-                    // would carry up to 1.2e-4 px at n = 4096, i.e. 2.4e-4/a in r^2, more than the margin for a < ~25 px.
-                    // With the difference rounded once, every term below has a relative error of a few 2^-24 and r^2 ~ 1
-                    // at the edge is good to ~5e-7.
-                    const float sxf = (float)g.p2, syf = (float)g.p3;
+                    // a whole pixel is certainly inside / outside; the 1e-5 margins cover the float rounding (the centre
+                    // is subtracted in double: (float)centre alone would carry up to 1.2e-4 px at n = 4096).  The pixels
+                    // of the thin band between them take their factor from the edge table built for this pass (one
+                    // load), or the exact (double) routine on the few lines the table does not cover.
+                    const float s_al = COL ? (float)g.p3 : (float)g.p2, s_cr = COL ? (float)g.p2 : (float)g.p3;
                     const float in5 = (float)g.p5 - 1e-5f, out6 = (float)g.p6 + 1e-5f;
-                    const float a0 = COL ? (float)((double)t - g.p1) * syf : (float)((double)t - g.p0) * sxf;
-                    const float da = COL ? (float)T * syf : (float)T * sxf;
-                    const float bq = COL ? (float)((double)line - g.p0) * sxf : (float)((double)line - g.p1) * syf;
-                    const float b2 = bq * bq;
+                    const float a0 = ellipse_a0(t, COL ? g.p1 : g.p0, s_al);
+                    const float da = __fmul_rn((float)T, s_al);
+                    const float b2 = ellipse_b2(line, COL ? g.p0 : g.p1, s_cr);
                     const bool obsc = g.flag != 0;
+                    unsigned emask = 0;
 #pragma unroll
                     for (int j = 0; j < E; ++j) {
-                        const float aq = fmaf((float)j, da, a0);
-                        const float r2 = aq * aq + b2;
+                        const float r2 = ellipse_r2(a0, da, j, b2);
                         if (r2 <= in5) {
                             if (obsc) v[j] = C<R>((R)0, (R)0);
                         } else if (r2 >= out6) {
                             if (!obsc) v[j] = C<R>((R)0, (R)0);
                         } else {
-#ifndef PAOS_EXP_NO_EDGE
-                            const int idx = t + j * T;
-                            double m, fi;
-                            gen_factor_slow(g, COL ? line : idx, COL ? idx : line, N, m, fi);
-                            v[j] = v[j] * (R)m;
-#endif
+                            emask |= 1u << j;
                         }
                     }
+#ifndef PAOS_EXP_NO_EDGE
+                    if (emask) {
+                        int4 hdr = make_int4(0, 0, 1 << 16, 0);
+                        const double* fac = nullptr;
+                        if (g.ptr0) {
+                            hdr = __ldg(reinterpret_cast<const int4*>(g.ptr0) + line);
+                            fac = reinterpret_cast<const double*>(reinterpret_cast<const char*>(g.ptr0) + (size_t)N * 16) +
+                                  (size_t)line * 2 * EDGE_CAP;
+                        }
+                        while (emask) {
+                            const int je = __ffs((int)emask) - 1;
+                            emask &= emask - 1;
+                            const int idx = t + je * T;
+                            double m;
+                            const unsigned k0 = (unsigned)(idx - hdr.x), k1 = (unsigned)(idx - hdr.y);
+                            if (k0 < (unsigned)(hdr.z & 0xff)) m = __ldg(fac + k0);
+                            else if (k1 < (unsigned)((hdr.z >> 8) & 0xff)) m = __ldg(fac + EDGE_CAP + k1);
+                            else {
+                                double fi;
+                                gen_factor_slow(g, COL ? line : idx, COL ? idx : line, N, m, fi);
+                            }
+#pragma unroll
+                            for (int j = 0; j < E; ++j)
+                                if (j == je) v[j] = v[j] * (R)m;
+                        }
+                    }
+#endif
                 } else if (g.kind == GEN_RECT) {
 #pragma unroll
                     for (int j = 0; j < E; ++j) {

@@ -182,6 +182,7 @@ struct Rec {
     bool col = false;
     PassParams P;                         // REC_PASS
     std::vector<TableSpec> specs;         // REC_TABLES
+    std::vector<EdgeSpec> edges;          // REC_TABLES: edge tables of the elliptical masks, built with the phase tables
     Norm2Item norm;                       // REC_NORM2
     std::function<int(cudaStream_t)> fn;  // REC_FN: anything else (screens, uploads, zero fill), run per handle
 };
@@ -329,6 +330,7 @@ struct PlannedPass {
 struct Plan {
     std::vector<PlannedPass> passes;
     std::vector<TableSpec> specs;
+    std::vector<EdgeSpec> edges;
 };
 
 static int spec_from_acc(paos_wfo* w, const PosAcc& a, Plan& plan, const void** tab_out) {
@@ -464,6 +466,25 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
             line_hi = std::min(line_hi, (int)std::floor(c0 + reach));
         }
         finish_pass(P, axis, line_lo, line_hi);
+        // edge tables: the exact overlap of the rim pixels of every elliptical mask of this pass, evaluated once by a
+        // small kernel instead of on the critical path of the lines that meet them (device_types.h: EdgeSpec)
+        static const bool edge_tables = getenv("PAOS_NO_EDGE_TABLES") == nullptr;
+        for (int gi = 0; gi < P.ngen && edge_tables; ++gi) {
+            GenOp& g = P.gen[gi];
+            if (g.kind != GEN_ELLIPSE) continue;
+            void* mem;
+            if (alloc_table(w, edge_table_bytes(w->n), &mem) != PAOS_OK) {
+                g_last_error.clear();
+                continue;  // pool exhausted: the pass kernel evaluates these pixels itself
+            }
+            EdgeSpec es{};
+            es.g = g;
+            es.out = mem;
+            es.col = axis == 1 ? 1 : 0;
+            es.T = w->n / geom_E(w->n);
+            plan.edges.push_back(es);
+            g.ptr0 = mem;
+        }
         for (int p = 0; p <= P.nfft; ++p) {
             P.scl[p] = 1.0;
             P.tab[p] = nullptr;
@@ -553,6 +574,19 @@ static int launch_pass_group(paos_wfo* lead, bool col, const PassParams* const* 
     return PAOS_OK;
 }
 
+static int launch_edge_tables(paos_wfo* lead, const std::vector<EdgeSpec>& edges, cudaStream_t st) {
+    for (size_t s = 0; s < edges.size(); s += EB_MAX) {
+        EdgeBlock B{};
+        B.n = lead->n;
+        B.nspec = (int)std::min<size_t>(EB_MAX, edges.size() - s);
+        for (int i = 0; i < B.nspec; ++i) B.spec[i] = edges[s + i];
+        cudaError_t e = launch_build_edge_tables(B, st);
+        if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "edge-table builder launch failed: %s", cudaGetErrorString(e));
+        lead->stats.kernel_launches++;
+    }
+    return PAOS_OK;
+}
+
 static int launch_tables(paos_wfo* lead, const std::vector<TableSpec>& specs, cudaStream_t st) {
     for (size_t s = 0; s < specs.size(); s += TB_MAX) {
         TableBlock B{};
@@ -589,16 +623,19 @@ static int do_pass(paos_wfo* w, bool col, const PassParams& P) {
     return launch_pass_group(w, col, &one, 1, w->stream);
 }
 
-static int do_tables(paos_wfo* w, std::vector<TableSpec>& specs) {
-    if (specs.empty()) return PAOS_OK;
+static int do_tables(paos_wfo* w, std::vector<TableSpec>& specs, const std::vector<EdgeSpec>* edges = nullptr) {
+    if (specs.empty() && (!edges || edges->empty())) return PAOS_OK;
     if (w->recording) {
         w->program.emplace_back();
         Rec& r = w->program.back();
         r.kind = REC_TABLES;
         r.specs = specs;
+        if (edges) r.edges = *edges;
         return PAOS_OK;
     }
-    return launch_tables(w, specs, w->stream);
+    int rc = launch_tables(w, specs, w->stream);
+    if (!rc && edges) rc = launch_edge_tables(w, *edges, w->stream);
+    return rc;
 }
 
 static int do_norm2(paos_wfo* w, const Norm2Item& item) {
@@ -631,6 +668,7 @@ static int execute_programs(paos_wfo** ws, int nb) {
     cudaStream_t st = lead->stream;
     std::vector<size_t> at((size_t)nb, 0);
     std::vector<TableSpec> specs;
+    std::vector<EdgeSpec> edges;
     std::vector<Norm2Item> norms;
     const PassParams* group[BMAX];
     for (;;) {
@@ -655,12 +693,14 @@ static int execute_programs(paos_wfo** ws, int nb) {
                 }
         } else if (n_tab) {
             specs.clear();
+            edges.clear();
             for (int b = 0; b < nb; ++b)
                 if (at[b] < ws[b]->program.size() && ws[b]->program[at[b]].kind == REC_TABLES) {
                     const Rec& r = ws[b]->program[at[b]++];
                     specs.insert(specs.end(), r.specs.begin(), r.specs.end());
+                    edges.insert(edges.end(), r.edges.begin(), r.edges.end());
                 }
-            if ((rc = launch_tables(lead, specs, st))) return rc;
+            if ((rc = launch_tables(lead, specs, st)) || (rc = launch_edge_tables(lead, edges, st))) return rc;
         } else if (n_norm) {
             norms.clear();
             for (int b = 0; b < nb; ++b)
@@ -700,7 +740,7 @@ static int ensure_pool(paos_wfo* w, size_t need_tables) {
 
 static int run_plan(paos_wfo* w, Plan& plan) {
     // tables first (one or more launches of the builder), then the passes
-    int rc = do_tables(w, plan.specs);
+    int rc = do_tables(w, plan.specs, &plan.edges);
     if (rc) return rc;
     for (PlannedPass& pp : plan.passes) {
         if ((rc = do_pass(w, pp.col, pp.P))) return rc;
@@ -714,8 +754,11 @@ static int flush_ops(paos_wfo* w, std::vector<Op>& ops, int readout, void* dst_r
     if (w->dropped) return fail(PAOS_ERR_STATE, "the field was discarded by a final read-out: reset the handle before re-using it");
     int rc = set_device(w);
     if (rc) return rc;
-    // worst case: every op opens two tables per axis
-    rc = ensure_pool(w, 4 * ops.size() + 8);
+    // worst case: every op opens two tables per axis; every elliptical mask adds an edge table
+    size_t ellipses = 0;
+    for (const Op& op : ops) ellipses += op.kind == OP_GEN && op.gen.kind == GEN_ELLIPSE;
+    const size_t per_table = (((size_t)w->n * w->elem) + 255) & ~(size_t)255;
+    rc = ensure_pool(w, 4 * ops.size() + 8 + ellipses * (edge_table_bytes(w->n) / per_table + 2));
     if (rc) return rc;
     w->tab_used = 0;
     Plan plan;

@@ -107,6 +107,9 @@ class Sweep:
         self.tdev = torch.device("cuda", self.device)
         self.rdtype = torch.float64 if dtype == "complex128" else torch.float32
         self.streams = [torch.cuda.Stream(device=self.tdev) for _ in range(slots)]
+        # device-to-host copies of finished results run on a stream of their own, so that a slot's next batch of kernels
+        # does not queue behind 8 x 32 MiB of PCIe traffic
+        self.copy_streams = [torch.cuda.Stream(device=self.tdev) for _ in range(slots)]
         # wfos[s][i]: wavefront i of slot s; all wavefronts of a slot share the slot's stream
         self.slot_wfos = [[WFO(1.0, 1.0e-6, self.n, 1.0, device=self.device, dtype=dtype, stream=s) for _ in range(self.batch)]
                           for s in self.streams]
@@ -217,6 +220,11 @@ class Sweep:
             last = res[max(res.keys())] if res else {}
             return {k2: v for k2, v in last.items() if k2 not in ("aperture", "wfe")}
 
+        # copies of whole read-outs into a host stack that holds every job go to the slot's copy stream (the source row of
+        # `out` is written once per sweep); ring buffers and staged windows stay ordered on the slot's own stream
+        side_copies = host_out is not None and stage is None and host_out.shape[0] >= len(jobs) and out.shape[0] >= len(jobs)
+        pending = [[] for _ in range(nslots)]
+
         def finish(k, job, wfo, stream, last, s=0, i=0):
             dst = out[k % out.shape[0]]
             if peak_out is not None:
@@ -236,8 +244,11 @@ class Sweep:
                     _lib.check(_lib.lib.paos_crop_convert(wfo._handle, C.c_void_p(dst.data_ptr()), x0, y0, nx, ny,
                                                           1 if host_out.dtype == torch.float32 else 0, C.c_void_p(st.data_ptr())))
                     dst = st
-                with torch.cuda.stream(stream):
-                    host_out[k % host_out.shape[0]].copy_(dst, non_blocking=True)
+                if side_copies:
+                    pending[s].append((k, dst))
+                else:
+                    with torch.cuda.stream(stream):
+                        host_out[k % host_out.shape[0]].copy_(dst, non_blocking=True)
 
         def do_group(s, ks):
             """Jobs ``ks`` (at most ``batch`` of them) on slot s."""
@@ -263,6 +274,15 @@ class Sweep:
                 if lasts[i] is None:
                     lasts[i] = python_driver(k, jobs[k], wfos[i])
                 finish(k, jobs[k], wfos[i], stream, lasts[i], s, i)
+            if pending[s]:
+                done = torch.cuda.Event()
+                done.record(stream)
+                cs = self.copy_streams[s]
+                cs.wait_event(done)
+                with torch.cuda.stream(cs):
+                    for k, dst in pending[s]:
+                        host_out[k].copy_(dst, non_blocking=True)
+                pending[s].clear()
             if on_group is not None:
                 ev = torch.cuda.Event()
                 ev.record(stream)
@@ -288,7 +308,7 @@ class Sweep:
         else:
             for g, ks in enumerate(groups):
                 do_group(g % nslots, ks)
-        for stream in self.streams:
+        for stream in self.streams + self.copy_streams:
             stream.synchronize()
         return out, meta
 

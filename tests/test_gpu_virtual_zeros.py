@@ -145,3 +145,46 @@ def test_sweep_slot_is_reusable_after_final_read_outs():
     assert np.array_equal(a, b.cpu().numpy())
     energy = a.sum(axis=(1, 2))  # normalised at the stop, then clipped by the apertures behind it
     assert np.all(energy > 0.1) and np.all(energy <= 1.0 + 1e-9), energy
+
+
+def test_edge_tables_do_not_change_a_bit(tmp_path):
+    """The rim pixels of an elliptical mask take their exact overlap from a table built once per pass (one lane per pixel)
+    instead of from the routine called by the lane that meets them; the factor is the same double either way, so every
+    output must be identical with PAOS_NO_EDGE_TABLES=1 (read once per process: the comparison runs in two children)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = """
+import sys, numpy as np
+sys.path.insert(0, %r)
+import paos_b200
+from paos_b200 import configs
+from paos_b200.sweep import Sweep
+out = []
+jobs = configs.airs_ch0(grid=512, n_wl=5) + configs.airs_ch0(grid=512, n_wl=3, wl_range=(0.8, 1.2))
+o, _ = Sweep(512, slots=1, what="amplitude", batch=4).run(jobs)
+out.append(o.cpu().numpy())
+w = paos_b200.WFO(1.0, 1e-6, 512, 4)
+for (xc, yc, hx, hy, ob) in [(0.0, 0.0, 0.5, 0.3, False), (0.05, -0.02, 0.1, 0.12, True), (0.3, 0.2, 0.02, 0.01, True), (1.9, 0.0, 0.4, 0.4, True)]:
+    w.aperture(xc, yc, hx=hx, hy=hy, obscuration=ob)
+    w._fft2()
+out.append(np.abs(w.wfo))
+job = configs.hubble(grid=256)[0]
+r = paos_b200.run(job["pupil_diameter"], job["wavelength"], 256, job["zoom"], job["field"], job["opt_chain"])
+out += [r[k]["amplitude"] for k in sorted(r)]
+np.savez(sys.argv[1], *out)
+""" % root
+    files = []
+    for tag, env in (("tables", {}), ("inline", {"PAOS_NO_EDGE_TABLES": "1"})):
+        path = str(tmp_path / f"{tag}.npz")
+        e = dict(os.environ)
+        e.update(env)
+        r = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True, env=e)
+        assert r.returncode == 0, r.stderr[-2000:]
+        files.append(np.load(path))
+    a, b = files
+    assert sorted(a.files) == sorted(b.files) and len(a.files) >= 5
+    for k in a.files:
+        assert np.array_equal(a[k], b[k]), k

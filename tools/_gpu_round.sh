@@ -1,7 +1,10 @@
 set -x
 cd $GRAFT_REPO_ROOT
-CMD="python bench.py --n-wl 16 --steps 1 --warmup 1 --no-cpu --slots 1"
-timeout 600 $CMD > gpurun_out/r02_plain.json 2> gpurun_out/r02_plain.err; echo "plain rc=$?"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches.csv $CMD > gpurun_out/r02_ncu1.log 2>&1; echo "ncu1 rc=$?"
-timeout 1200 ncu --set full --import-source on --clock-control none -k regex:pass_kernel -s 14 -c 14 -f -o gpurun_out/r02_prof $CMD > gpurun_out/r02_ncu2.log 2>&1; echo "ncu2 rc=$?"
-ls -la gpurun_out | tail -8
+timeout 1800 python -m pytest tests -m gpu -q -x > gpurun_out/r02i_pytest.log 2>&1; echo "pytest rc=$?"
+tail -6 gpurun_out/r02i_pytest.log
+for v in on off; do
+  if [ $v = off ]; then export PAOS_NO_EDGE_TABLES=1; else unset PAOS_NO_EDGE_TABLES; fi
+  timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/r02i_bench_$v.json 2> gpurun_out/r02i_bench_$v.err; echo "bench $v rc=$?"
+  python -c "
+import json;d=json.load(open('gpurun_out/r02i_bench_$v.json'));print('$v','value',d['value'],'roof',d['roofline']['frac'],'launches',d['gpu_launches']); print({k:round(v['avg_us']) for k,v in d['passes'].items()})"
+done
