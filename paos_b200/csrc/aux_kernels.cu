@@ -104,8 +104,8 @@ cudaError_t launch_build_tables(const TableBlock& B, cudaStream_t st) {
 __global__ void __launch_bounds__(256) build_edge_tables_kernel(const __grid_constant__ EdgeBlock B) {
     const EdgeSpec& sp = B.spec[blockIdx.y];
     const GenOp& g = sp.g;
-    const int n = B.n, lane = threadIdx.x & 31, line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (line >= n) return;
+    const int n = B.n, lane = threadIdx.x & 31, line = sp.line_lo + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (line >= n || line > sp.line_hi) return;  // lines outside [line_lo, line_hi] hold no rim pixel and are never looked up
     const bool col = sp.col != 0;
     const int T = sp.T;
     const double c_al = col ? g.p1 : g.p0, c_cr = col ? g.p0 : g.p1;
@@ -159,7 +159,9 @@ __global__ void __launch_bounds__(256) build_edge_tables_kernel(const __grid_con
 
 cudaError_t launch_build_edge_tables(const EdgeBlock& B, cudaStream_t st) {
     if (B.nspec < 1) return cudaSuccess;
-    dim3 grid((B.n + 7) / 8, B.nspec);
+    int lines = 1;
+    for (int i = 0; i < B.nspec; ++i) lines = max(lines, B.spec[i].line_hi - B.spec[i].line_lo + 1);
+    dim3 grid((lines + 7) / 8, B.nspec);
     build_edge_tables_kernel<<<grid, 256, 0, st>>>(B);
     return cudaGetLastError();
 }
@@ -181,13 +183,16 @@ struct Norm2Batch {
 };
 static_assert(sizeof(Norm2Batch) <= 32764, "Norm2Batch must fit the kernel parameter space");
 
+// (256, 4): without the bound the inlined exact-overlap routine takes 203 registers, one CTA per SM, and the 9 472 mostly
+// empty CTAs of a batched reduction run in 64 waves (116 us); its rare path may spill
 template <typename R>
-__global__ void __launch_bounds__(256) norm2_partial_kernel(const __grid_constant__ Norm2Batch B) {
+__global__ void __launch_bounds__(256, 4) norm2_partial_kernel(const __grid_constant__ Norm2Batch B) {
     const Norm2Params& P = B.p[blockIdx.y];
     double* __restrict__ partials = B.partials[blockIdx.y];
     const int n = P.n;
     const C<R>* src = reinterpret_cast<const C<R>*>(P.src);
     double acc = 0.0;
+    bool any_row = false;  // CTA-uniform
     // one row per CTA step (32-bit index math; the 64-bit div/mod of a flat index cost more than the mask itself)
     for (int iy = blockIdx.x; iy < n; iy += gridDim.x) {
         // a row that misses the bounding box of an elliptical aperture contributes nothing
@@ -200,11 +205,16 @@ __global__ void __launch_bounds__(256) norm2_partial_kernel(const __grid_constan
             }
         }
         if (blank) continue;
+        any_row = true;
         for (int ix = threadIdx.x; ix < n; ix += blockDim.x) {
             C<R> v = src ? ldc(src + (size_t)iy * n + ix) : C<R>((R)1, (R)0);
             for (int g = 0; g < P.ngen; ++g) apply_gen(v, P.gen[g], ix, iy, n);
             acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
         }
+    }
+    if (!any_row) {  // every row of this CTA is blanked by an aperture: nothing to reduce
+        if (threadIdx.x == 0) partials[blockIdx.x] = 0.0;
+        return;
     }
     __shared__ double red[256];
     red[threadIdx.x] = acc;

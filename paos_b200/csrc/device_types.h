@@ -13,7 +13,8 @@ constexpr int TB_MAX = 64;  // tables built by one launch of the table builder (
 // general elementwise factors (real masks, phase screens, device scalars)
 enum GenKind : int {
     GEN_NONE = 0,
-    GEN_ELLIPSE = 1,    // exact pixel/ellipse overlap (theta = 0): p0=xc p1=yc p2=1/a p3=1/b p4=a*b; ptr0 = edge table or null
+    GEN_ELLIPSE = 1,    // exact pixel/ellipse overlap (theta = 0): p0=xc p1=yc p2=1/a p3=1/b p4=a*b; ptr0 = edge table or null,
+                        // valid for lines p7..p8
     GEN_RECT = 2,       // 32x32 sub-pixel rectangle: ptr0 = x counts, ptr1 = y counts (double[N])
     GEN_SCREEN = 3,     // exp(i*(2*pi*w)/wl): ptr0 = w (double[N*N]), p0 = wl
     GEN_SCALE_DEV = 4,  // multiply by *ptr0 (double in device memory)
@@ -112,8 +113,10 @@ struct EdgeSpec {
     void* out;
     int col;  // 1: lines are columns (line = ix, along = iy)
     int T;    // threads per line of the pass kernel: element idx = t + j * T, classified as the kernel does
+    int line_lo, line_hi;  // lines that can hold rim pixels (the ellipse's extent across the lines, two lines of slack); the
+                           // same bounds travel in g.p7, g.p8 of the GenOp the pass kernel gets, which looks up nothing outside
 };
-constexpr int EB_MAX = 32;
+constexpr int EB_MAX = 64;
 struct EdgeBlock {
     int n;
     int nspec;

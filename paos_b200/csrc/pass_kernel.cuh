@@ -224,10 +224,27 @@ __device__ __forceinline__ void apply_gen(C<R>& v, const GenOp& g, int ix, int i
             const float uq = (float)((double)ix - g.p0) * (float)g.p2, wq = (float)((double)iy - g.p1) * (float)g.p3;
             const float r2 = uq * uq + wq * wq;
             double m;
+            bool from_table = false;
             if (r2 <= (float)g.p5 - 1e-5f) m = 1.0;
             else if (r2 >= (float)g.p6 + 1e-5f) m = 0.0;
-            else m = ellipse_fraction(g, (double)ix, (double)iy);
-            re = g.flag ? 1.0 - m : m;
+            else {
+                m = 0.0;
+                if (g.ptr0 && iy >= (int)g.p7 && iy <= (int)g.p8) {  // row-axis edge table built for this reduction (EdgeSpec); holds the final factor
+                    const int4 hdr = __ldg(reinterpret_cast<const int4*>(g.ptr0) + iy);
+                    const double* fac = reinterpret_cast<const double*>(reinterpret_cast<const char*>(g.ptr0) + (size_t)n * 16) +
+                                        (size_t)iy * 2 * EDGE_CAP;
+                    const unsigned k0 = (unsigned)(ix - hdr.x), k1 = (unsigned)(ix - hdr.y);
+                    if (k0 < (unsigned)(hdr.z & 0xff)) {
+                        m = __ldg(fac + k0);
+                        from_table = true;
+                    } else if (k1 < (unsigned)((hdr.z >> 8) & 0xff)) {
+                        m = __ldg(fac + EDGE_CAP + k1);
+                        from_table = true;
+                    }
+                }
+                if (!from_table) m = ellipse_fraction(g, (double)ix, (double)iy);
+            }
+            re = from_table ? m : (g.flag ? 1.0 - m : m);
         } break;
         case GEN_RECT: {
             const double cx = __ldg((const double*)g.ptr0 + ix), cy = __ldg((const double*)g.ptr1 + iy);
@@ -414,7 +431,7 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
                     if (emask) {
                         int4 hdr = make_int4(0, 0, 1 << 16, 0);
                         const double* fac = nullptr;
-                        if (g.ptr0) {
+                        if (g.ptr0 && line >= (int)g.p7 && line <= (int)g.p8) {
                             hdr = __ldg(reinterpret_cast<const int4*>(g.ptr0) + line);
                             fac = reinterpret_cast<const double*>(reinterpret_cast<const char*>(g.ptr0) + (size_t)N * 16) +
                                   (size_t)line * 2 * EDGE_CAP;

@@ -333,6 +333,28 @@ struct Plan {
     std::vector<EdgeSpec> edges;
 };
 
+// edge table of elliptical mask g for a pass along `axis` (0 rows, 1 columns): where it goes and which lines it covers
+static EdgeSpec make_edge_spec(const paos_wfo* w, GenOp& g, void* mem, int axis) {
+    const double c_cr = axis == 1 ? g.p0 : g.p1, s_cr = axis == 1 ? g.p2 : g.p3;
+    const double reach = (std::sqrt(g.p6) + 1e-3) / s_cr + 2.0;
+    int lo = 0, hi = w->n - 1;
+    if (std::isfinite(reach) && std::isfinite(c_cr)) {
+        lo = (int)std::max(0.0, std::min((double)w->n, std::floor(c_cr - reach)));
+        hi = (int)std::min((double)(w->n - 1), std::max(-1.0, std::ceil(c_cr + reach)));
+    }
+    g.ptr0 = mem;
+    g.p7 = (double)lo;
+    g.p8 = (double)hi;
+    EdgeSpec es{};
+    es.g = g;
+    es.out = mem;
+    es.col = axis == 1 ? 1 : 0;
+    es.T = w->n / geom_E(w->n);
+    es.line_lo = lo;
+    es.line_hi = hi;
+    return es;
+}
+
 static int spec_from_acc(paos_wfo* w, const PosAcc& a, Plan& plan, const void** tab_out) {
     void* mem;
     int rc = alloc_table(w, (size_t)w->n * w->elem, &mem);
@@ -477,13 +499,7 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
                 g_last_error.clear();
                 continue;  // pool exhausted: the pass kernel evaluates these pixels itself
             }
-            EdgeSpec es{};
-            es.g = g;
-            es.out = mem;
-            es.col = axis == 1 ? 1 : 0;
-            es.T = w->n / geom_E(w->n);
-            plan.edges.push_back(es);
-            g.ptr0 = mem;
+            plan.edges.push_back(make_edge_spec(w, g, mem, axis));
         }
         for (int p = 0; p <= P.nfft; ++p) {
             P.scl[p] = 1.0;
@@ -758,7 +774,8 @@ static int flush_ops(paos_wfo* w, std::vector<Op>& ops, int readout, void* dst_r
     size_t ellipses = 0;
     for (const Op& op : ops) ellipses += op.kind == OP_GEN && op.gen.kind == GEN_ELLIPSE;
     const size_t per_table = (((size_t)w->n * w->elem) + 255) & ~(size_t)255;
-    rc = ensure_pool(w, 4 * ops.size() + 8 + ellipses * (edge_table_bytes(w->n) / per_table + 2));
+    // (+ room for the edge tables of a stop reduction that may follow this flush, so that it never has to grow the pool)
+    rc = ensure_pool(w, 4 * ops.size() + 8 + (ellipses + (size_t)GMAX) * (edge_table_bytes(w->n) / per_table + 2));
     if (rc) return rc;
     w->tab_used = 0;
     Plan plan;
@@ -1281,6 +1298,27 @@ int paos_wfo_make_stop(paos_wfo* w) {
     }
     w->ops = tail;
     if (w->materialized && (rc = materialize_band(w, w->field, w->band))) return rc;
+    // The reduction multiplies every pixel by the folded masks; the rim pixels of the elliptical ones take their exact overlap
+    // from row-axis edge tables built right before it (one lane per rim pixel) instead of one serial evaluation per mask
+    // and rim pixel inside the reduction (which made it 124 us per batch of 8 wavefronts).  The tables sit behind those of
+    // the flush above in the pool; the next flush reuses the memory in stream order.
+    static const bool edge_tables = getenv("PAOS_NO_EDGE_TABLES") == nullptr;
+    if (edge_tables) {
+        std::vector<EdgeSpec> edges;
+        const size_t per_table = (((size_t)w->n * w->elem) + 255) & ~(size_t)255;
+        size_t ellipses = 0;
+        for (const GenOp& g : gens) ellipses += g.kind == GEN_ELLIPSE;
+        if (ellipses && ensure_pool(w, w->tab_used / per_table + 1 + ellipses * (edge_table_bytes(w->n) / per_table + 2)) == PAOS_OK) {
+            for (GenOp& g : gens) {
+                if (g.kind != GEN_ELLIPSE) continue;
+                void* mem;
+                if (alloc_table(w, edge_table_bytes(w->n), &mem) != PAOS_OK) break;
+                edges.push_back(make_edge_spec(w, g, mem, 0));
+            }
+            std::vector<TableSpec> none;
+            if ((rc = do_tables(w, none, &edges))) return rc;
+        }
+    }
     double* slot = w->slots + 2 * (w->slot_next++ % paos_wfo::NSLOTS);
     Norm2Item item{};
     item.src = w->materialized ? w->field : nullptr;
