@@ -1,7 +1,17 @@
 // device_types.h -- plain structs shared by the host planner and the CUDA kernels.
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only: the encoder is fetched from the driver at run time, nothing links libcuda)
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+// TMA tiles for the field loads / stores of the column passes (pass_kernel.cuh: use_tma_field): on by default for grids of
+// PAOS_TMA_FIELD_MIN_N and up; -DPAOS_TMA_FIELD=0 builds the direct-access variant for the A/B measurement.
+#ifndef PAOS_TMA_FIELD
+#define PAOS_TMA_FIELD 1
+#endif
+#ifndef PAOS_TMA_FIELD_MIN_N
+#define PAOS_TMA_FIELD_MIN_N 2048
+#endif
 
 namespace paosb {
 
@@ -61,6 +71,8 @@ struct PassParams {
     int zero_fill;             // 1: blank tiles store zeros into the field (diagnostic mode PAOS_ZERO_FILL=1)
     int tile_base;             // set by the launcher: tile of CTA 0 (blank tiles are not launched unless they have to store)
     int pad;
+    const void* tmap_host;     // host pointer to the CUtensorMap of `dst` (column tiles of W complex x 256 rows), or null; the
+                               // launcher copies it into BatchParams::tmap (a tensor map must sit in kernel parameter space)
     void* dst_real;
     GenOp gen[GMAX];
 };
@@ -73,9 +85,10 @@ struct PassParams {
 constexpr int BMAX = 16;
 template <int CAP> struct BatchParams {
     int nb;
-    int pad;
+    int use_tmap;  // 1: every item carries a tensor map of its field (column kernels: TMA tile stores)
     int start[CAP + 2];
     PassParams p[CAP];
+    CUtensorMap tmap[CAP];
 };
 static_assert(sizeof(BatchParams<BMAX>) <= 32764, "BatchParams must fit the kernel parameter space");
 

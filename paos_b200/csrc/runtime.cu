@@ -216,6 +216,7 @@ struct paos_wfo {
     bool recording = false;
     std::vector<Rec> program;
     std::vector<void*> retired_pools;  // table pools outgrown while recording: still referenced by the program
+    std::map<const void*, CUtensorMap*> tmaps;  // tensor maps of the field buffers (column tiles), built on first use
 
     paos_stats stats{};
     bool timing = false;
@@ -230,6 +231,49 @@ struct paos_wfo {
 static int set_device(paos_wfo* w) {
     CU(cudaSetDevice(w->device));
     return PAOS_OK;
+}
+
+// Tensor map of an n x n complex field for the column passes' TMA tile stores: a 2-D tensor of reals (2n per row), boxes of
+// 2W reals x 256 rows.  cuTensorMapEncodeTiled is fetched from the driver at run time (no link against libcuda); null when
+// the variant is not compiled in or the driver refuses.
+static const CUtensorMap* field_tmap(paos_wfo* w, const void* field) {
+#if PAOS_TMA_FIELD
+    if (w->n < PAOS_TMA_FIELD_MIN_N || !field) return nullptr;
+    auto it = w->tmaps.find(field);
+    if (it != w->tmaps.end()) return it->second;
+    typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Encode encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+        cudaGetLastError();
+        return (Encode)fn;
+    }();
+    CUtensorMap* tm = nullptr;
+    if (encode) {
+        const int W = tile_width(w->n, w->dtype, true);
+        const bool c128 = w->dtype == PAOS_C128;
+        const cuuint64_t gdim[2] = {(cuuint64_t)2 * w->n, (cuuint64_t)w->n};
+        const cuuint64_t gstride[1] = {(cuuint64_t)w->n * w->elem};
+        const cuuint32_t box[2] = {(cuuint32_t)(2 * W), 256u};
+        const cuuint32_t estr[2] = {1u, 1u};
+        tm = new CUtensorMap;
+        CUresult r = encode(tm, c128 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(field), gdim, gstride, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            delete tm;
+            tm = nullptr;
+        }
+    }
+    w->tmaps[field] = tm;  // null is remembered too: the direct stores are used
+    return tm;
+#else
+    (void)w;
+    (void)field;
+    return nullptr;
+#endif
 }
 
 static int alloc_table(paos_wfo* w, size_t bytes, void** out) {
@@ -512,6 +556,7 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
                 if (rc) return rc;
             }
         }
+        if (axis == 1) P.tmap_host = field_tmap(w, field);
         PlannedPass pp;
         pp.col = axis == 1;
         pp.P = P;
@@ -941,6 +986,7 @@ int paos_wfo_destroy(paos_wfo* w) {
     if (w->scratch_field) cudaFree(w->scratch_field);
     if (w->tab_pool) cudaFree(w->tab_pool);
     for (void* p : w->retired_pools) cudaFree(p);
+    for (auto& kv : w->tmaps) delete kv.second;
     if (w->partials) cudaFree(w->partials);
     if (w->slots) cudaFree(w->slots);
     if (w->own_field && w->field) cudaFree(w->field);
