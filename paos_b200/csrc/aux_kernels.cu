@@ -1,5 +1,7 @@
 // aux_kernels.cu -- the small kernels around the line passes: separable phase tables, the stop
 // reduction, read-out (|.|, angle, |.|^2), the Zernike screen, PSD helpers.
+#include <memory>
+
 #include "aux_kernels.h"
 #include "pass_kernel.cuh"
 
@@ -246,7 +248,9 @@ __global__ void norm2_final_kernel(const __grid_constant__ Norm2Batch B, int np)
 
 cudaError_t launch_norm2_batch(const Norm2Item* items, int nb, int n, int dtype, int npartials, cudaStream_t st) {
     if (nb < 1 || nb > BMAX) return cudaErrorInvalidValue;
-    static thread_local Norm2Batch B;
+    static thread_local std::unique_ptr<Norm2Batch> holder;  // 21 KB: heap, not thread-local storage
+    if (!holder) holder.reset(new Norm2Batch());
+    Norm2Batch& B = *holder;
     B.nb = nb;
     for (int b = 0; b < nb; ++b) {
         B.partials[b] = items[b].partials;

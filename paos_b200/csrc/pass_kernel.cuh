@@ -12,6 +12,7 @@
 #pragma once
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 
 #include "device_types.h"
 #include "fft_core.cuh"
@@ -676,7 +677,11 @@ cudaError_t launch_pass_cap(const PassParams* const* Ps, int nb, const void* tw1
         if (e != cudaSuccess) return e;
         configured[device & 63] = true;
     }
-    static thread_local BatchParams<CAP> BP;
+    // the parameter block is 1.8 KB (CAP = 1) or 28 KB (CAP = 16): kept on the heap behind a thread-local pointer, so that threads
+    // that never launch (the planner threads of a batch) do not pay for ~1 MB of thread-local storage per instantiation set
+    static thread_local std::unique_ptr<BatchParams<CAP>> holder;
+    if (!holder) holder.reset(new BatchParams<CAP>());
+    BatchParams<CAP>& BP = *holder;
     int total = 0, used = 0;
     bool all_maps = use_tma_field<N, COL>();
     for (int i = 0; i < nb; ++i) {
