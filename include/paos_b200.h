@@ -248,7 +248,9 @@ int paos_chain_run(paos_wfo *w, double pupil_diameter, double wavelength, double
  * handles one by one.
  *
  * paos_wfo_begin_record: from now on the handle records its device work instead of launching it (host-blocking calls --
- * paos_wfo_read, paos_wfo_sync, paos_zernike_cov, the *_host_out arguments -- fail with PAOS_ERR_STATE meanwhile).
+ * paos_wfo_read, paos_wfo_sync, paos_zernike_cov, the *_host_out arguments -- fail with PAOS_ERR_STATE meanwhile).  Host
+ * arrays handed to a recording handle (screens, masks, PSD noise) are read when the batch executes: keep them alive until
+ * paos_batch_execute has returned.
  * paos_batch_execute: plans what is still queued on each handle and executes the recorded programs of nb <=
  * paos_batch_capacity() handles in lockstep on their common stream (same grid size, precision, device and stream
  * required); the handles leave recording mode.  Asynchronous.  On error every handle of the batch is reset to a

@@ -295,6 +295,16 @@ static int get_screen(paos_wfo* w, double** out) {
     return PAOS_OK;
 }
 
+// A screen that is written immediately (not through a deferred record) while the handle is recording must not come from the
+// recycled pool: passes recorded earlier, not yet executed, may still read those buffers.  Such a screen gets memory of its
+// own, released at the next paos_wfo_sync / destroy.
+static int get_screen_for_immediate_write(paos_wfo* w, double** out) {
+    if (!w->recording) return get_screen(w, out);
+    CU(cudaMalloc((void**)out, (size_t)w->n * w->n * sizeof(double)));
+    w->retired_pools.push_back(*out);
+    return PAOS_OK;
+}
+
 static void recycle_screens(paos_wfo* w) {
     // every consumer of a busy screen has been enqueued; later writers are ordered behind them on the stream
     for (double* p : w->screens_busy) w->screens_free.push_back(p);
@@ -1880,7 +1890,7 @@ extern "C" int paos_wfo_grid_sag(paos_wfo* w, const double* host_sag, const unsi
     if ((rc = set_device(w))) return rc;
     const size_t nn = (size_t)w->n * w->n;
     double* screen;
-    if ((rc = get_screen(w, &screen))) return rc;
+    if ((rc = get_screen_for_immediate_write(w, &screen))) return rc;
     DevBuf dmask;
     if (mask_host_out) CU(dmask.alloc(nn));
     if ((rc = prepare_grid_sag(w, host_sag, host_mask, nx, ny, delx, dely, xdec, ydec, dx, dy, screen, dmask.as<unsigned char>()))) return rc;
@@ -1919,7 +1929,7 @@ static int chain_grid_sag(paos_wfo* w, const paos_surface& s, double dx, double 
     if ((rc = set_device(w))) return rc;
     if (s.sag_key == 0) {
         double* screen;
-        if ((rc = get_screen(w, &screen))) return rc;
+        if ((rc = get_screen_for_immediate_write(w, &screen))) return rc;
         if ((rc = prepare_grid_sag(w, s.sag, s.sag_mask, s.sag_nx, s.sag_ny, s.sag_delx, s.sag_dely, s.sag_xdec, s.sag_ydec, dx, dy, screen, nullptr)))
             return rc;
         return paos_wfo_phase_screen_device(w, screen, wl);
