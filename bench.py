@@ -664,6 +664,119 @@ def run_ours(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations (--config): same contract, their own workload line
+# ---------------------------------------------------------------------------------------------------
+CONFIGS = {
+    # name: (grid, what the workload line says, job builder(world) -> (jobs, psd noise provider or None))
+    "hubble": (1024, "Hubble_simple.ini as shipped (1024^2, 1.0 um, on-axis), IMAGE_PLANE |.|^2 only, 256 propagations per GPU",
+               lambda cfg, world: ((lambda base: [dict(base) for _ in range(256 * world)])(cfg.hubble(light_output=True)[0]), None)),
+    "fgs1": (512, "Ariel_FGS-FGS1.ini + wfe_realization_SN20210914.csv, 256 Monte-Carlo WFE realizations per GPU at 512^2, 36 Zernike terms",
+             lambda cfg, world: (cfg.fgs1_montecarlo(grid=512, realizations=range(256 * world)), None)),
+    "ta_psd": (1024, "lens_file_TA_Ground_PSD.ini, 9 fields x 28 wavelengths per GPU at 1024^2, PSD screens drawn on the device (Philox)",
+               lambda cfg, world: ([j for _ in range(world) for j in cfg.ta_ground_psd(grid=1024, n_wl=28)], None)),
+    "grid_sag": (4096, "test_Grid_Sag.ini, synthetic on-grid sag at 4096^2 complex128, 12 wavelengths per GPU (map prepared on the device)",
+                 lambda cfg, world: (cfg.grid_sag(grid=4096, wavelengths=tuple([0.55, 3.0, 7.8] * (4 * world))), None)),
+}
+
+
+def run_config(args):
+    """One of the non-headline BASELINE.json configurations through the same front-end: device-resident PSF/s (`value`), end to
+    end with every PSF copied to pinned host memory (`e2e`), parity of a few jobs against the CPU arm in the same run."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from paos_b200 import configs as cfg
+    from paos_b200 import sweep as sweep_mod
+
+    grid, workload, make = CONFIGS[args.config]
+    jobs_all, noise = make(cfg, world)
+    blocks = sweep_mod.partition(jobs_all, world)
+    lo, hi = blocks[rank]
+    jobs = jobs_all[lo:hi]
+    sw = sweep_mod.Sweep(grid, device=local_rank, dtype=args.dtype, slots=args.slots, what="psf", batch=args.batch)
+    stack = sw.empty_stack(len(jobs))
+    host = sw.empty_stack(len(jobs), host=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        sw.run(jobs, out=stack)
+    barrier()
+    st0 = sw.stats()
+    sampler.mark()
+    ms = max_over_ranks(timed_steps(torch, sw, jobs, stack, None, args.steps))
+    clocks = sampler.stop() if rank == 0 else None
+    st1 = sw.stats()
+    sw.run(jobs, out=stack, host_out=host)
+    barrier()
+    ms_e2e = max_over_ranks(timed_steps(torch, sw, jobs, stack, host, args.steps))
+    total = len(jobs_all) * args.steps
+    # the same sweep when the native surface records of the jobs are kept between sweeps (Sweep.run's default): at small grids
+    # the Python record builder (~0.25 ms per job under the GIL) is what a sweep over fresh jobs waits for, not the device
+    global CACHE_COMPILED
+    keep, CACHE_COMPILED = CACHE_COMPILED, True
+    sw.run(jobs, out=stack)
+    barrier()
+    ms_cached = max_over_ranks(timed_steps(torch, sw, jobs, stack, None, args.steps))
+    CACHE_COMPILED = keep
+    parity = None
+    if rank == 0 and not args.no_cpu and args.config != "ta_psd":  # device-drawn PSD noise has no CPU counterpart (statistical mode)
+        from oracle import paos_np
+
+        pick = [0, len(jobs) // 2] if grid <= 1024 else [0]
+        worst = 0.0
+        for k in pick:
+            j = jobs[k]
+            ref = paos_np.run(j["pupil_diameter"], j["wavelength"], j["gridsize"], j["zoom"], j["field"], j["opt_chain"])
+            psf_ref = ref[max(ref)]["amplitude"] ** 2
+            worst = max(worst, float(np.max(np.abs(host[k].numpy() - psf_ref)) / np.max(psf_ref)))
+        tol = 1e-10 if args.dtype == "complex128" else 1e-4
+        parity = {"n": len(pick), "worst_psf": worst, "tolerance": tol, "ok": bool(worst <= tol), "against": "oracle/paos_np.py (port)"}
+        if not parity["ok"]:
+            raise SystemExit(f"PARITY FAILURE inside bench.py --config {args.config}: {json.dumps(parity)}")
+    if rank == 0:
+        rbytes = 8 if args.dtype == "complex128" else 4
+        emit({
+            "metric": f"{grid}^2 fp64 PSFs/sec (full surface chain, {args.config})", "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64" if args.dtype == "complex128" else "f32", "data": "synthetic",
+            "config": {"workload": workload, "grid": grid, "psf_per_step": len(jobs_all), "slots": len(sw.streams), "batch": sw.batch},
+            "clocks": clocks,
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": int(len(jobs_all) * grid * grid * rbytes)},
+            "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]) * world,
+            "passes_per_psf": (st1["passes_planned"] - st0["passes_planned"]) / (len(jobs) * args.steps),
+            "pass_launches_per_psf": (st1["pass_launches"] - st0["pass_launches"]) / (len(jobs) * args.steps),
+            "value_records_kept": {"value": total / (ms_cached * 1e-3), "unit": UNIT,
+                                   "note": "compiled surface records kept between sweeps (Sweep.run default); `value` rebuilds them every sweep"},
+            "parity": parity, "roofline": None, "cpu_baseline": None,
+        })
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 _JSON_FD = None
 
 
@@ -698,6 +811,8 @@ def main():
     ap.add_argument("--slots", type=int, default=None, help="host threads / streams (default: 3 batched, 4 unbatched)")
     ap.add_argument("--batch", type=int, default=None, help="wavefronts per batched launch (default by grid size; 1 = unbatched)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--config", default="airs_ch0", choices=["airs_ch0"] + sorted(CONFIGS),
+                    help="workload: airs_ch0 = BASELINE.json configs[1] (the headline, default); the others are its configs[0], [2], [3], [4]")
     ap.add_argument("--cache-compiled", action="store_true", help="diagnostic: keep the compiled surface records between sweeps")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
@@ -710,6 +825,8 @@ def main():
     claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config != "airs_ch0":
+        return run_config(args)
     return run_ours(args)
 
 

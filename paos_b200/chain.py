@@ -58,6 +58,27 @@ class ChainArgs(C.Structure):
     ]
 
 
+_NAN = float("nan")
+_ZTABLES = {}
+
+
+def _zernike_tables(K, ordering, normalize):
+    """``(m, n, norms)`` of the first K polynomials as contiguous int32 / float64 arrays, computed once per (K, ordering,
+    normalize): a Monte-Carlo sweep compiles the same tables for every realization."""
+    key = (int(K), str(ordering), str(normalize))
+    hit = _ZTABLES.get(key)
+    if hit is None:
+        m, n = j2mn(K, ordering)
+        hit = (np.ascontiguousarray(m, dtype=np.int32), np.ascontiguousarray(n, dtype=np.int32),
+               np.ascontiguousarray(zernike_norms(m, n, normalize), dtype=np.float64))
+        if len(_ZTABLES) < 256:
+            _ZTABLES[key] = hit
+    return hit
+
+
+_D4 = C.c_double * 4
+
+
 class CompiledChain:
     """``paos_surface`` array of one job plus the host arrays it points to (kept alive here)."""
 
@@ -89,11 +110,10 @@ class CompiledChain:
                 s.ap_shape = _SHAPES[ap["shape"]]
                 s.ap_obscuration = 0 if ap["type"] == "aperture" else 1
                 s.ap_xrad, s.ap_yrad, s.ap_xc, s.ap_yc = float(ap["xrad"]), float(ap["yrad"]), float(ap["xc"]), float(ap["yc"])
-            t, sg = item["ABCDt"](), item["ABCDs"]()
-            s.abcd_t[:] = [float(t[0, 0]), float(t[0, 1]), float(t[1, 0]), float(t[1, 1])]
-            s.abcd_s[:] = [float(sg[0, 0]), float(sg[0, 1]), float(sg[1, 0]), float(sg[1, 1])]
-            s.cout_t = float(item["ABCDt"].cout)
-            s.zernike_radius = float("nan")
+            s.abcd_t = _D4(*item["ABCDt"]._ABCD.ravel().tolist())
+            s.abcd_s = _D4(*item["ABCDs"]._ABCD.ravel().tolist())
+            s.cout_t = float(item["ABCDt"]._cout)
+            s.zernike_radius = _NAN
             if s.type == SURF_COORDBREAK:
                 s.xdec, s.ydec, s.xrot, s.yrot = (float(item[k]) for k in ("xdec", "ydec", "xrot", "yrot"))
             elif s.type == SURF_ZERNIKE:
@@ -104,9 +124,8 @@ class CompiledChain:
                 index = np.asarray(item["Zindex"])
                 assert not np.any(np.diff(index) - 1), "Zernike sequence should be continuous"
                 K = len(index)
-                m, n = j2mn(K, item["Zordering"])
-                coef = np.ascontiguousarray(np.asarray(item["Z"], dtype=np.float64) * zernike_norms(m, n, item["Znormalize"]))
-                m32, n32 = np.ascontiguousarray(m, dtype=np.int32), np.ascontiguousarray(n, dtype=np.int32)
+                m32, n32, norms = _zernike_tables(K, item["Zordering"], item["Znormalize"])
+                coef = np.ascontiguousarray(np.asarray(item["Z"], dtype=np.float64) * norms)
                 self.keep += [coef, m32, n32]
                 s.zernike_terms = K
                 s.zernike_origin = 0 if item["Zorigin"] == "x" else 1
