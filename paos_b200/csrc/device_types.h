@@ -73,6 +73,7 @@ struct PassParams {
     int pad;
     const void* tmap_host;     // host pointer to the CUtensorMap of `dst` (column tiles of W complex x 256 rows), or null; the
                                // launcher copies it into BatchParams::tmap (a tensor map must sit in kernel parameter space)
+    const void* tmap_real_host;  // same for `dst_real` (tiles of W reals x 256 rows) when a read-out is fused into the pass
     void* dst_real;
     GenOp gen[GMAX];
 };
@@ -85,10 +86,12 @@ struct PassParams {
 constexpr int BMAX = 16;
 template <int CAP> struct BatchParams {
     int nb;
-    int use_tmap;  // 1: every item carries a tensor map of its field (column kernels: TMA tile stores)
+    int use_tmap;  // bit 0: every item carries a tensor map of its field (column kernels: TMA tile loads / stores);
+                   // bit 1: every item carries one of its read-out destination as well
     int start[CAP + 2];
     PassParams p[CAP];
     CUtensorMap tmap[CAP];
+    CUtensorMap tmap_real[CAP];
 };
 static_assert(sizeof(BatchParams<BMAX>) <= 32764, "BatchParams must fit the kernel parameter space");
 

@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
     C<R> v[E];
     bool loaded = false;
     if constexpr (kTmaField) {
-        if (src && BP.use_tmap) {
+        if (src && (BP.use_tmap & 1)) {
             // the live rows [in_lo, in_hi] of this CTA's W columns arrive as TMA boxes of W x 256 rows in the exchange buffer
             // (idle until the first transform); the threads then pick their elements with conflict-free shared loads
             const int base = P.in_lo, rows = P.in_hi < N ? P.in_hi - base + 1 : 0;  // empty band: in_lo = in_hi = N
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
     // let the next kernel of the stream get its CTAs scheduled while this grid stores (it waits for our completion above)
     asm volatile("griddepcontrol.launch_dependents;");
     if constexpr (use_tma_field<N, COL>()) {
-        if (dst && BP.use_tmap && !P.readout) {
+        if (dst && (BP.use_tmap & 1) && !P.readout) {
             // tile [row][W] in the exchange buffer, then W x 256-row boxes to the TMA unit
             __syncthreads();  // every thread is done with the exchange data of the last transform
 #pragma unroll
@@ -646,6 +646,25 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
             const int idx = t + j * T;
             const size_t ga = COL ? ((size_t)idx * N + line) : ((size_t)line * N + idx);
             stc_stream(dst + ga, v[j]);
+        }
+    }
+    if constexpr (use_tma_field<N, COL>()) {
+        if (P.readout && (BP.use_tmap & 2)) {
+            // fused read-out through a TMA tile of W reals per row, like the field above
+            R* rt = reinterpret_cast<R*>(smem_raw);
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < E; ++j)
+                rt[(size_t)(t + j * T) * W + w] = (P.readout == 3) ? v[j].x * v[j].x + v[j].y * v[j].y : readout_value<R>(v[j], P.readout);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+#pragma unroll 1
+                for (int r0 = 0; r0 < N; r0 += TMA_BOX_ROWS) tma_store_tile(&BP.tmap_real[b], rt + (size_t)r0 * W, tile * W, r0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            return;
         }
     }
     if (P.readout) {
@@ -683,7 +702,7 @@ cudaError_t launch_pass_cap(const PassParams* const* Ps, int nb, const void* tw1
     if (!holder) holder.reset(new BatchParams<CAP>());
     BatchParams<CAP>& BP = *holder;
     int total = 0, used = 0;
-    bool all_maps = use_tma_field<N, COL>();
+    bool all_maps = use_tma_field<N, COL>(), all_real = use_tma_field<N, COL>();
     for (int i = 0; i < nb; ++i) {
         // blank tiles have nothing to do unless they must store zeros (fused read-out, diagnostic zero fill): launch the rest
         PassParams& P = BP.p[used];
@@ -697,11 +716,13 @@ cudaError_t launch_pass_cap(const PassParams* const* Ps, int nb, const void* tw1
         }
         if (all_maps && P.tmap_host) std::memcpy(&BP.tmap[used], P.tmap_host, sizeof(CUtensorMap));
         else all_maps = false;
+        if (all_real && P.readout && P.tmap_real_host) std::memcpy(&BP.tmap_real[used], P.tmap_real_host, sizeof(CUtensorMap));
+        else all_real = false;
         BP.start[used] = total;
         total += tiles;
         ++used;
     }
-    BP.use_tmap = all_maps ? 1 : 0;
+    BP.use_tmap = (all_maps ? 1 : 0) | (all_real ? 2 : 0);
     if (used == 0) return cudaSuccess;
     BP.nb = used;
     BP.start[used] = total;

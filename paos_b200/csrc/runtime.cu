@@ -236,11 +236,15 @@ static int set_device(paos_wfo* w) {
 // Tensor map of an n x n complex field for the column passes' TMA tile stores: a 2-D tensor of reals (2n per row), boxes of
 // 2W reals x 256 rows.  cuTensorMapEncodeTiled is fetched from the driver at run time (no link against libcuda); null when
 // the variant is not compiled in or the driver refuses.
-static const CUtensorMap* field_tmap(paos_wfo* w, const void* field) {
+static const CUtensorMap* field_tmap(paos_wfo* w, const void* field, bool real_readout = false) {
 #if PAOS_TMA_FIELD
     if (w->n < PAOS_TMA_FIELD_MIN_N || !field) return nullptr;
     auto it = w->tmaps.find(field);
     if (it != w->tmaps.end()) return it->second;
+    if (w->tmaps.size() > 4096) {  // read-out destinations come and go: keep the cache bounded
+        for (auto& kv : w->tmaps) delete kv.second;
+        w->tmaps.clear();
+    }
     typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static Encode encode = [] {
@@ -254,9 +258,10 @@ static const CUtensorMap* field_tmap(paos_wfo* w, const void* field) {
     if (encode) {
         const int W = tile_width(w->n, w->dtype, true);
         const bool c128 = w->dtype == PAOS_C128;
-        const cuuint64_t gdim[2] = {(cuuint64_t)2 * w->n, (cuuint64_t)w->n};
-        const cuuint64_t gstride[1] = {(cuuint64_t)w->n * w->elem};
-        const cuuint32_t box[2] = {(cuuint32_t)(2 * W), 256u};
+        const int per = real_readout ? 1 : 2;  // reals per pixel: a read-out (|.|, angle, |.|^2) or the complex field
+        const cuuint64_t gdim[2] = {(cuuint64_t)per * w->n, (cuuint64_t)w->n};
+        const cuuint64_t gstride[1] = {(cuuint64_t)w->n * (w->elem / 2) * per};
+        const cuuint32_t box[2] = {(cuuint32_t)(per * W), 256u};
         const cuuint32_t estr[2] = {1u, 1u};
         tm = new CUtensorMap;
         CUresult r = encode(tm, c128 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(field), gdim, gstride, box,
@@ -600,6 +605,7 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
     if (readout && !plan.passes.empty()) {
         plan.passes.back().P.readout = readout;
         plan.passes.back().P.dst_real = dst_real;
+        if (plan.passes.back().col) plan.passes.back().P.tmap_real_host = field_tmap(w, dst_real, true);
     }
     return PAOS_OK;
 }
