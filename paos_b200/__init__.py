@@ -18,5 +18,5 @@ from .zernike import PolyOrthoNorm, Zernike, j2mn, mn2j  # noqa: F401
 from .psd import PSD  # noqa: F401
 from .parse_config import parse_config  # noqa: F401
 from .raytrace import raytrace  # noqa: F401
-from .pipeline import pipeline  # noqa: F401
+from .pipeline import pipeline, wfe_sweep  # noqa: F401
 from .save_output import load_output, save_datacube, save_output  # noqa: F401

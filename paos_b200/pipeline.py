@@ -42,6 +42,47 @@ def setup_chains(passvalue):
     return pup, params, wavelengths, fields[0], opt_chains
 
 
+def parse_wfe_columns(spec):
+    """``"file,c"`` (the reference's form, ``pipeline.py:118``) or ``"file,c0-c1"`` / ``"file,c0:c1:step"`` for a range of
+    realizations.  Returns ``(file, [columns])``; a range includes both ends, a slice excludes the stop."""
+    wfe_file, _, col = spec.partition(",")
+    col = col.strip()
+    if ":" in col:
+        parts = [int(float(v)) for v in col.split(":")]
+        return wfe_file, list(range(*parts))
+    if "-" in col.lstrip("-"):
+        a, b = col.split("-", 1)
+        return wfe_file, list(range(int(float(a)), int(float(b)) + 1))
+    return wfe_file, [int(float(col))]
+
+
+def wfe_sweep(passvalue, what="psf", out=None, **sweep_kw):
+    """Monte-Carlo front-end (BASELINE.json configs[2]): every WFE realization of ``passvalue["wfe"]`` (a column, a range
+    ``c0-c1`` or a slice ``c0:c1[:step]``) times every wavelength of the lens file, IMAGE_PLANE only, through
+    :class:`paos_b200.sweep.Sweep` -- the realizations of a batch share their kernel launches.  Returns
+    ``(stack, meta, index)``: the device stack ``[n_jobs, N, N]``, one dict of host scalars per job, and ``index[k] =
+    (realization, wavelength_um)``.  Extra keywords go to ``Sweep.run`` (``host_out``, ``ee``, ``peak_out``, ...)."""
+    from .sweep import Sweep
+
+    wfe_file, columns = parse_wfe_columns(passvalue["wfe"])
+    table = np.genfromtxt(wfe_file, delimiter=",", comments="#")
+    jobs, index = [], []
+    for c in columns:
+        pup, params, wavelengths, fields, opt_chains = parse_config(passvalue["conf"])
+        coeffs = np.append(np.zeros(3), table[:, c + 3] * 1.0e-9)
+        for wl, chain in zip(wavelengths, opt_chains):
+            for item in chain.values():
+                item["save"] = item["name"] == "IMAGE_PLANE"
+                if item["name"] == "Z1":
+                    item.update(Zordering="standard", Znormalize="True", Zorigin="x", Z=coeffs, Zindex=np.arange(len(coeffs)))
+            jobs.append(dict(pupil_diameter=pup, wavelength=1.0e-6 * wl, gridsize=params["grid_size"], zoom=params["zoom"],
+                             field=fields[0], opt_chain=chain, tag=f"r{c}/w{wl:g}"))
+            index.append((c, wl))
+    sw = Sweep(jobs[0]["gridsize"], device=passvalue.get("device", 0), dtype=passvalue.get("dtype", "complex128"), what=what)
+    stack, meta = sw.run(jobs, out=out, **sweep_kw)
+    return stack, meta, index
+
+
 def pipeline(passvalue):
     """Run the POP of every wavelength of a lens file; returns the list of ``run`` result dictionaries (one per wavelength)
     when ``passvalue['return']`` is true, else ``None``."""

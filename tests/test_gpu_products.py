@@ -113,3 +113,36 @@ def test_pipeline_default_call_saves_the_datacube(tmp_path, data_dir):
         paos_b200.pipeline({"conf": conf})  # save=True needs an output name, as in the reference
     with pytest.raises(NotImplementedError):
         paos_b200.pipeline({"conf": conf, "save": False, "plot": True})
+
+
+def test_wfe_sweep_over_a_range_of_realizations(data_dir, tmp_path):
+    """-wfe with a column range: every realization x wavelength through the batch front-end; realization c of
+    the range equals the reference-style single-column pipeline call for that c."""
+    import os
+    import shutil
+
+    import paos_b200
+
+    conf = str(tmp_path / "fgs1.ini")
+    text = open(os.path.join(data_dir, "Ariel_FGS-FGS1.ini")).read()
+    lines, section = [], None
+    for ln in text.splitlines():
+        if ln.startswith("["):
+            section = ln.strip()
+        if section == "[general]" and ln.startswith("grid_size"):
+            ln = "grid_size = 256"
+        if section == "[lens_13]" and ln.startswith("ignore"):
+            ln = "ignore = False"
+        lines.append(ln)
+    open(conf, "w").write("\n".join(lines) + "\n")
+    wfe = os.path.join(data_dir, "wfe_realization_SN20210914.csv")
+    stack, meta, index = paos_b200.wfe_sweep({"conf": conf, "wfe": f"{wfe},2-4"})
+    n_wl = len(paos_b200.parse_config(conf)[2])
+    assert stack.shape[0] == 3 * n_wl and [c for c, _ in index][::n_wl] == [2, 3, 4]
+    single = paos_b200.pipeline({"conf": conf, "wfe": f"{wfe},3", "light_output": True, "save": False, "return": True})
+    for k in range(n_wl):
+        ret = single[k]
+        ref = ret[max(ret)]["amplitude"] ** 2
+        got = stack[n_wl + k].cpu().numpy()
+        assert np.max(np.abs(got - ref)) <= 1e-12 * ref.max()
+    assert not np.array_equal(stack[0].cpu().numpy(), stack[n_wl].cpu().numpy())

@@ -301,3 +301,12 @@ def test_pipeline_chain_setup_and_refusals():
         paos_b200.pipeline({"conf": conf})  # save defaults to True, as in the reference: it needs passvalue['output']
     with pytest.raises(NotImplementedError):
         paos_b200.pipeline({"conf": conf, "save": False, "plot": True})
+
+
+def test_wfe_column_ranges():
+    from paos_b200.pipeline import parse_wfe_columns
+
+    assert parse_wfe_columns("a.csv,7") == ("a.csv", [7])
+    assert parse_wfe_columns("a.csv,3-6") == ("a.csv", [3, 4, 5, 6])
+    assert parse_wfe_columns("dir/a.csv,0:10:4") == ("dir/a.csv", [0, 4, 8])
+    assert parse_wfe_columns("a.csv,2.0") == ("a.csv", [2])
