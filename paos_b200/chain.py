@@ -76,7 +76,10 @@ def _zernike_tables(K, ordering, normalize):
     return hit
 
 
-_D4 = C.c_double * 4
+# numpy view of the two 2 x 2 matrices inside the paos_surface records: the ctypes array is filled in two vectorised writes
+# instead of two ctypes array constructions per surface (which were 60 % of the time of building the records)
+_ABCD_VIEW = np.dtype({"names": ["abcd_t", "abcd_s"], "formats": [("f8", (4,)), ("f8", (4,))],
+                       "offsets": [Surface.abcd_t.offset, Surface.abcd_s.offset], "itemsize": C.sizeof(Surface)})
 
 
 class CompiledChain:
@@ -110,8 +113,6 @@ class CompiledChain:
                 s.ap_shape = _SHAPES[ap["shape"]]
                 s.ap_obscuration = 0 if ap["type"] == "aperture" else 1
                 s.ap_xrad, s.ap_yrad, s.ap_xc, s.ap_yc = float(ap["xrad"]), float(ap["yrad"]), float(ap["xc"]), float(ap["yc"])
-            s.abcd_t = _D4(*item["ABCDt"]._ABCD.ravel().tolist())
-            s.abcd_s = _D4(*item["ABCDs"]._ABCD.ravel().tolist())
             s.cout_t = float(item["ABCDt"]._cout)
             s.zernike_radius = _NAN
             if s.type == SURF_COORDBREAK:
@@ -158,6 +159,10 @@ class CompiledChain:
                     self.keep += [n1, n2]
                     s.psd_noise1 = n1.ctypes.data_as(C.POINTER(C.c_double))
                     s.psd_noise2 = n2.ctypes.data_as(C.POINTER(C.c_double))
+        if self.count:
+            view = np.frombuffer(self.array, dtype=_ABCD_VIEW, count=self.count)
+            view["abcd_t"] = np.array([item["ABCDt"]._ABCD for item in items], dtype=np.float64).reshape(self.count, 4)
+            view["abcd_s"] = np.array([item["ABCDs"]._ABCD for item in items], dtype=np.float64).reshape(self.count, 4)
         self.snapshots = (Snapshot * max(len(self.saved), 1))()
         self.final = Snapshot()
         self.nsnap = C.c_int(0)
