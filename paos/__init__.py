@@ -7,19 +7,18 @@ the reference on ``sys.path``).  It holds no logic of its own.
 """
 import logging
 
+import paos_b200 as _impl
 from paos_b200 import __version__  # noqa: F401
 
 __pkg_name__ = __title__ = "PAOS"
 __author__ = "paos_b200"
 logger = logging.getLogger("paos_b200")
 
-from paos.classes.abcd import ABCD  # noqa: E402,F401
-from paos.classes.psd import PSD  # noqa: E402,F401
-from paos.classes.wfo import WFO  # noqa: E402,F401
-from paos.classes.zernike import PolyOrthoNorm, Zernike  # noqa: E402,F401
-from paos.core.coordinateBreak import coordinate_break  # noqa: E402,F401
-from paos.core.parseConfig import parse_config  # noqa: E402,F401
+# the public names of the reference package, bound to the device implementation
+for _name in ("ABCD", "PSD", "WFO", "PolyOrthoNorm", "Zernike", "coordinate_break", "parse_config", "raytrace", "run",
+              "save_datacube", "save_output"):
+    globals()[_name] = getattr(_impl, _name)
+del _name
+
+from paos import classes, core, util  # noqa: E402,F401  (sub-packages with the reference's module paths)
 from paos.core.plot import plot_pop  # noqa: E402,F401
-from paos.core.raytrace import raytrace  # noqa: E402,F401
-from paos.core.run import run  # noqa: E402,F401
-from paos.core.saveOutput import save_datacube, save_output  # noqa: E402,F401

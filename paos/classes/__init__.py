@@ -1,1 +1,2 @@
 """``paos.classes``: module paths of the reference (``paos/classes/``) mapped onto ``paos_b200``."""
+from paos.classes import abcd, psd, wfo, zernike  # noqa: F401
