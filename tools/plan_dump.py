@@ -1,5 +1,8 @@
 """Print the fused pass plan (PAOS_DEBUG_PLAN=1) and per-kind pass timings of one AIRS-CH0 2048^2 job."""
-import sys; sys.path.insert(0,'/root/repo')
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import paos_b200
 from paos_b200 import configs
 from paos_b200.sweep import Sweep
