@@ -6,7 +6,7 @@ namespace paosb {
 
 #ifdef PAOS_EXP_ROW2  // experiment: two rows per CTA (256 threads, 2 CTAs/SM) like the column kernel
 #define PAOS_ROW_2048 PAOS_CASE(2048, 16, 2, 2, 2, 2)
-#else
+#else  // (five row CTAs per SM would need 96 registers: 1.7 KB of spills per thread, measured slower in round 1)
 #define PAOS_ROW_2048 PAOS_CASE(2048, 16, 1, 2, 4, 2)
 #endif
 // 512^2: five 128-thread CTAs per SM (96 registers; measured +3-4 % over four at 128 registers, six spill and lose 8 %)
