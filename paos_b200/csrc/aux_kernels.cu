@@ -195,6 +195,17 @@ __global__ void __launch_bounds__(256, 4) norm2_partial_kernel(const __grid_cons
     const C<R>* src = reinterpret_cast<const C<R>*>(P.src);
     double acc = 0.0;
     bool any_row = false;  // CTA-uniform
+    // columns outside the bounding box of an elliptical aperture contribute exact zeros as well: a zoom-4 pupil covers a
+    // quarter of the row (same FP32 test, in the along-row coordinate, as the one that blanks rows below)
+    int x_lo = 0, x_hi = n - 1;
+    for (int g = 0; g < P.ngen; ++g) {
+        const GenOp& gg = P.gen[g];
+        if (gg.kind == GEN_ELLIPSE && !gg.flag) {
+            const double half = sqrt(gg.p6 + 2e-5) / gg.p2 + 1.0;  // a pixel further out certainly fails r^2 < p6 + 1e-5
+            x_lo = max(x_lo, (int)floor(gg.p0 - half));
+            x_hi = min(x_hi, (int)ceil(gg.p0 + half));
+        }
+    }
     // one row per CTA step (32-bit index math; the 64-bit div/mod of a flat index cost more than the mask itself)
     for (int iy = blockIdx.x; iy < n; iy += gridDim.x) {
         // a row that misses the bounding box of an elliptical aperture contributes nothing
@@ -208,7 +219,7 @@ __global__ void __launch_bounds__(256, 4) norm2_partial_kernel(const __grid_cons
         }
         if (blank) continue;
         any_row = true;
-        for (int ix = threadIdx.x; ix < n; ix += blockDim.x) {
+        for (int ix = x_lo + (int)threadIdx.x; ix <= x_hi; ix += blockDim.x) {
             C<R> v = src ? ldc(src + (size_t)iy * n + ix) : C<R>((R)1, (R)0);
             for (int g = 0; g < P.ngen; ++g) apply_gen(v, P.gen[g], ix, iy, n);
             acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;

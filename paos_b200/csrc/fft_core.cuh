@@ -173,10 +173,33 @@ template <int N_, int E_> struct LineGeom {
 // line (0..T-1).  sm: this line's exchange buffer.  tw1/tw2: twiddle tables.  SYNC: barrier functor
 // covering all threads of the line.
 // FIRST_SYNC = false: the caller has already passed a barrier since the last read of the exchange buffer.
-template <typename G, typename R, typename SYNC, bool FIRST_SYNC = true>
+//
+// In-place exchanges (three-stage sizes, PAOS_INPLACE_EXCHANGE): a barrier is needed after every write of the exchange
+// buffer (the readers are other threads), but the two barriers *before* the writes only guard against overwriting
+// elements somebody still has to read -- and they disappear if every thread writes exactly the addresses it has just
+// read itself.  The middle stage does so by construction (its R2-point butterflies put their results back where the
+// operands came from); the first write of the NEXT transform does so if it uses the layout the last read of THIS
+// transform left, so consecutive transforms of a pass alternate between two layouts of the buffer (flip = 0 / 1):
+//
+//   flip 0: stage-1 write  sm[k1][t]              middle read+write  sm[q + R2 c][n2 E + n3]    last read  sm[n3][q E + m]
+//   flip 1: stage-1 write  sm[n3][q E + k1]       middle read+write  sm[n3][n2 E + q + R2 c]    last read  sm[m][t]
+//
+// with t = q E + n3.  Rows are TP = T + 1 (odd) elements long, so the eight lanes of a 16-byte shared-memory phase
+// (consecutive t, hence consecutive n3 or consecutive columns) hit eight different bank groups in all six patterns.
+// Two barriers per transform instead of four; the arithmetic and its order are unchanged (results are bit-identical).
+// MID is called by every thread right after the first barrier (the column kernels start the bulk copy of the next
+// phase table there: every thread has consumed the current one before its stage-1 butterfly).
+#ifndef PAOS_INPLACE_EXCHANGE
+#define PAOS_INPLACE_EXCHANGE 1
+#endif
+struct NoMid {
+    __device__ __forceinline__ void operator()() const {}
+};
+template <typename G, typename R, typename SYNC, bool FIRST_SYNC = true, typename MID = NoMid>
 __device__ __forceinline__ void line_fft_fwd(C<R>* v, int t, C<R>* sm, const C<R>* __restrict__ tw1,
-                                             const C<R>* __restrict__ tw2, SYNC sync) {
+                                             const C<R>* __restrict__ tw2, SYNC sync, int flip = 0, MID mid = MID()) {
     constexpr int E = G::E, T = G::T, R2 = G::R2, TP = G::TP;
+    constexpr bool INPLACE = PAOS_INPLACE_EXCHANGE != 0 && R2 > 1;
     // stage 1: radix-E over j, twiddle W_N^(k1*t)
 #ifndef PAOS_TABLE_TWIDDLES
     // load only the power-of-two twiddles (issued before the butterfly so their latency hides behind it) and
@@ -198,12 +221,76 @@ __device__ __forceinline__ void line_fft_fwd(C<R>* v, int t, C<R>* sm, const C<R
 #pragma unroll
     for (int k1 = 1; k1 < E; ++k1) v[k1] = v[k1] * ldc_ro(tw1 + (k1 - 1) * T + t);
 #endif
+    if constexpr (INPLACE) {
+        const int n3 = t % E, q = t / E;
+        C<R>* const a0 = sm + t;                 // flip 0: stage-1 write, flip 1: last read   (stride TP)
+        C<R>* const a1 = sm + n3 * TP + q * E;   // flip 1: stage-1 write, flip 0: last read   (stride 1)
+        constexpr int NB = E / R2;               // butterflies per thread
+#ifndef PAOS_EXP_NO_SMEM
+        if (!flip) {
+#pragma unroll
+            for (int k1 = 0; k1 < E; ++k1) stc(a0 + k1 * TP, v[k1]);
+        } else {
+#pragma unroll
+            for (int k1 = 0; k1 < E; ++k1) stc(a1 + k1, v[k1]);
+        }
+        sync();
+        mid();
+        C<R>* const m0 = sm + q * TP + n3;  // flip 0: + c R2 TP + n2 E
+        C<R>* const m1 = sm + n3 * TP + q;  // flip 1: + c R2    + n2 E
+        if (!flip) {
+#pragma unroll
+            for (int c = 0; c < NB; ++c)
+#pragma unroll
+                for (int n2 = 0; n2 < R2; ++n2) v[c * R2 + n2] = ldc(m0 + c * R2 * TP + n2 * E);
+        } else {
+#pragma unroll
+            for (int c = 0; c < NB; ++c)
+#pragma unroll
+                for (int n2 = 0; n2 < R2; ++n2) v[c * R2 + n2] = ldc(m1 + c * R2 + n2 * E);
+        }
+#endif
+#pragma unroll
+        for (int c = 0; c < NB; ++c) dft<R2>(v + c * R2);
+#pragma unroll
+        for (int k2 = 1; k2 < R2; ++k2) {
+            C<R> w = ldc_ro(tw2 + (k2 - 1) * E + n3);
+#pragma unroll
+#ifndef PAOS_EXP_NO_DP
+            for (int c = 0; c < NB; ++c) v[c * R2 + k2] = v[c * R2 + k2] * w;
+#endif
+        }
+#ifndef PAOS_EXP_NO_SMEM
+        if (!flip) {
+#pragma unroll
+            for (int c = 0; c < NB; ++c)
+#pragma unroll
+                for (int k2 = 0; k2 < R2; ++k2) stc(m0 + c * R2 * TP + k2 * E, v[c * R2 + k2]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < NB; ++c)
+#pragma unroll
+                for (int k2 = 0; k2 < R2; ++k2) stc(m1 + c * R2 + k2 * E, v[c * R2 + k2]);
+        }
+        sync();
+        if (!flip) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = ldc(a1 + m);
+        } else {
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = ldc(a0 + m * TP);
+        }
+#endif
+        dft<E>(v);
+        return;
+    }
 #ifndef PAOS_EXP_NO_SMEM
     if constexpr (FIRST_SYNC) sync();  // previous readers of the buffer are done
 #pragma unroll
     for (int k1 = 0; k1 < E; ++k1) stc(sm + k1 * TP + t, v[k1]);
     sync();
 #endif
+    mid();
     if constexpr (R2 == 1) {
         // two-stage: thread p = k1 gathers A[p][n3]
 #pragma unroll

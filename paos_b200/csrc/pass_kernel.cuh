@@ -376,6 +376,8 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(kTmaTables ? tabbuf + N : tabbuf);
     unsigned tab_phase = 0;
     constexpr bool kTmaField = use_tma_field<N, COL>();
+    constexpr bool kInplace = PAOS_INPLACE_EXCHANGE != 0 && G::R2 > 1;  // two barriers per transform (fft_core.cuh)
+    int flip = 0;
     if constexpr (kTmaTables || kTmaField) {
         if (tid == 0) {
             mbar_init(mbar, 1);      // phase table of the next position
@@ -432,6 +434,8 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
                 v[j] = ((unsigned)(idx - P.in_lo) <= span && rows > 0) ? ldc(smem + (size_t)(idx - base) * W + w) : C<R>((R)0, (R)0);
             }
             loaded = true;
+            // the in-place transforms write the exchange buffer without a barrier of their own in front
+            if constexpr (kInplace) __syncthreads();
         }
     }
     if (loaded) {
@@ -570,49 +574,45 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
             }
         }
         if (pos == P.nfft) break;
+        // one forward line transform of the registers (inlined into both direction branches below)
+        auto transform = [&] {
+            if constexpr (kTmaTables) {
+                // the copy engine fetches the table of the next position while this transform runs; the buffer is free once
+                // every thread has consumed the staged table, i.e. after any barrier that follows the multiply above
+                auto next_table = [&] {
+                    if (tid == 0 && P.tab[pos + 1]) bulk_load(tabbuf, P.tab[pos + 1], (unsigned)(N * sizeof(C<R>)), mbar);
+                };
+                if constexpr (kInplace) {
+                    line_fft_fwd<G, R, decltype(sync), false, decltype(next_table)>(v, t, sm, tw1, tw2, sync, flip, next_table);
+                } else {
+                    __syncthreads();
+                    next_table();
+                    line_fft_fwd<G, R, decltype(sync), false>(v, t, sm, tw1, tw2, sync);
+                }
+            } else {
+                // pull the next position's phase table into L1 while this transform runs (one 128-byte line per
+                // prefetch; the table is N complex values, shared by every line of the pass)
+                const char* nxt = reinterpret_cast<const char*>(P.tab[pos + 1]);
+                if (nxt) {
+                    constexpr int LINES = N * (int)sizeof(C<R>) / 128;
+#pragma unroll
+                    for (int i = t; i < LINES; i += T) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + (size_t)i * 128));
+                }
+                line_fft_fwd<G, R>(v, t, sm, tw1, tw2, sync, flip);
+            }
+        };
         // the inverse transform is the forward one on swapped (re, im); with the direction known at compile time
         // inside each branch the swaps are register renaming, not moves
         if (P.dir[pos] < 0) {
 #pragma unroll
             for (int j = 0; j < E; ++j) v[j] = C<R>(v[j].y, v[j].x);
-            if constexpr (kTmaTables) {
-                // every thread has consumed the staged table (and the previous exchange): the buffer is free for the
-                // table of the next position, fetched by the copy engine while this transform runs
-                __syncthreads();
-                if (tid == 0 && P.tab[pos + 1]) bulk_load(tabbuf, P.tab[pos + 1], (unsigned)(N * sizeof(C<R>)), mbar);
-                line_fft_fwd<G, R, decltype(sync), false>(v, t, sm, tw1, tw2, sync);
-            } else {
-                // pull the next position's phase table into L1 while this transform runs (one 128-byte line per
-                // prefetch; the table is N complex values, shared by every line of the pass)
-                const char* nxt = reinterpret_cast<const char*>(P.tab[pos + 1]);
-                if (nxt) {
-                    constexpr int LINES = N * (int)sizeof(C<R>) / 128;
-#pragma unroll
-                    for (int i = t; i < LINES; i += T) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + (size_t)i * 128));
-                }
-                line_fft_fwd<G, R>(v, t, sm, tw1, tw2, sync);
-            }
+            transform();
 #pragma unroll
             for (int j = 0; j < E; ++j) v[j] = C<R>(v[j].y, v[j].x);
         } else {
-            if constexpr (kTmaTables) {
-                // every thread has consumed the staged table (and the previous exchange): the buffer is free for the
-                // table of the next position, fetched by the copy engine while this transform runs
-                __syncthreads();
-                if (tid == 0 && P.tab[pos + 1]) bulk_load(tabbuf, P.tab[pos + 1], (unsigned)(N * sizeof(C<R>)), mbar);
-                line_fft_fwd<G, R, decltype(sync), false>(v, t, sm, tw1, tw2, sync);
-            } else {
-                // pull the next position's phase table into L1 while this transform runs (one 128-byte line per
-                // prefetch; the table is N complex values, shared by every line of the pass)
-                const char* nxt = reinterpret_cast<const char*>(P.tab[pos + 1]);
-                if (nxt) {
-                    constexpr int LINES = N * (int)sizeof(C<R>) / 128;
-#pragma unroll
-                    for (int i = t; i < LINES; i += T) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + (size_t)i * 128));
-                }
-                line_fft_fwd<G, R>(v, t, sm, tw1, tw2, sync);
-            }
+            transform();
         }
+        flip ^= 1;  // consecutive transforms alternate between the two layouts of the exchange buffer (fft_core.cuh)
     }
     if (P.ctab_out) {
         const C<R> c = ldc_ro(reinterpret_cast<const C<R>*>(P.ctab_out) + line);
