@@ -70,6 +70,8 @@ struct PassParams {
     int readout;               // 0: store the complex field; PAOS_READ_* (1..3): store a real read-out into dst_real instead
     int zero_fill;             // 1: blank tiles store zeros into the field (diagnostic mode PAOS_ZERO_FILL=1)
     int tile_base;             // set by the launcher: tile of CTA 0 (blank tiles are not launched unless they have to store)
+    int out_lo, out_hi;        // along-line index range the NEXT pass of the plan will read (its tile range: it runs along the
+                               // other axis and touches nothing else); elements outside are not stored -- they stay stale
     int pad;
     const void* tmap_host;     // host pointer to the CUtensorMap of `dst` (column tiles of W complex x 256 rows), or null; the
                                // launcher copies it into BatchParams::tmap (a tensor map must sit in kernel parameter space)

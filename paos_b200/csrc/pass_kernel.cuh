@@ -625,15 +625,21 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
     if constexpr (use_tma_field<N, COL>()) {
         if (dst && (BP.use_tmap & 1) && !P.readout) {
             // tile [row][W] in the exchange buffer, then W x 256-row boxes to the TMA unit
+            // only the boxes that hold rows [out_lo, out_hi] leave: the next pass reads nothing else (device_types.h)
+            const int box_lo = P.out_lo / TMA_BOX_ROWS, box_hi = P.out_hi < N ? P.out_hi / TMA_BOX_ROWS : -1;
             __syncthreads();  // every thread is done with the exchange data of the last transform
 #pragma unroll
-            for (int j = 0; j < E; ++j) stc(smem + (size_t)(t + j * T) * W + w, v[j]);
+            for (int j = 0; j < E; ++j) {
+                const int bx = (t + j * T) / TMA_BOX_ROWS;
+                if (bx >= box_lo && bx <= box_hi) stc(smem + (size_t)(t + j * T) * W + w, v[j]);
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
             if (tid == 0) {
                 constexpr int REALS = (int)(sizeof(C<R>) / sizeof(R));  // tensor-map elements per complex value
 #pragma unroll 1
-                for (int r0 = 0; r0 < N; r0 += TMA_BOX_ROWS) tma_store_tile(&BP.tmap[b], smem + (size_t)r0 * W, tile * W * REALS, r0);
+                for (int r0 = box_lo * TMA_BOX_ROWS; r0 <= box_hi * TMA_BOX_ROWS; r0 += TMA_BOX_ROWS)
+                    tma_store_tile(&BP.tmap[b], smem + (size_t)r0 * W, tile * W * REALS, r0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile has left shared memory
             }
@@ -641,11 +647,12 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
         }
     }
     if (dst) {  // null: a final read-out, the field itself is not needed any more
+        const unsigned ospan = (unsigned)(P.out_hi - P.out_lo);  // the stretch the next pass reads (device_types.h)
 #pragma unroll
         for (int j = 0; j < E; ++j) {
             const int idx = t + j * T;
             const size_t ga = COL ? ((size_t)idx * N + line) : ((size_t)line * N + idx);
-            stc_stream(dst + ga, v[j]);
+            if ((unsigned)(idx - P.out_lo) <= ospan) stc_stream(dst + ga, v[j]);
         }
     }
     if constexpr (use_tma_field<N, COL>()) {

@@ -439,6 +439,8 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
         const int n = w->n;
         P.in_lo = 0;
         P.in_hi = n - 1;
+        P.out_lo = 0;
+        P.out_hi = n - 1;
         if (band.valid && P.src) {
             if (band.axis == axis) {  // lines outside the band are zero on input, hence on output
                 line_lo = std::max(line_lo, band.lo);
@@ -591,6 +593,22 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
         pp.P = P;
         plan.passes.push_back(pp);
     }
+    // Look ahead: a pass followed, inside this plan, by a pass along the other axis is read by that pass only, and that
+    // pass touches nothing outside its tile range (its blank tiles are neither loaded nor stored).  Along the lines of the
+    // first pass that range is a stretch of indices: only that stretch is stored (a zoom-4 beam: a quarter to 40 % of
+    // every line).  The last pass of a plan stores everything: whoever reads the field next is not known here.
+    static const bool store_ahead = getenv("PAOS_NO_STORE_RANGE") == nullptr;
+    for (size_t i = 0; store_ahead && !zero_fill && i + 1 < plan.passes.size(); ++i) {
+        PlannedPass& a = plan.passes[i];
+        const PlannedPass& b = plan.passes[i + 1];
+        if (a.col == b.col || !a.P.dst || b.P.src != a.P.dst || b.P.zero_fill) continue;
+        if (b.P.tile_lo <= 0 && b.P.tile_hi == 0x7fffffff) continue;
+        const int n = w->n, Wb = tile_width(n, w->dtype, b.col);
+        const int lo = std::max(0, b.P.tile_lo) * Wb;
+        const int hi = b.P.tile_hi < 0 ? -1 : (int)std::min<long long>(n - 1, (long long)b.P.tile_hi * Wb + Wb - 1);
+        a.P.out_lo = hi >= lo ? lo : n;  // empty: [n, n] matches no index
+        a.P.out_hi = hi >= lo ? hi : n;
+    }
     static const bool debug_plan = getenv("PAOS_DEBUG_PLAN") != nullptr;
     if (debug_plan) {
         for (const PlannedPass& pp : plan.passes) {
@@ -598,8 +616,9 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
             for (int p2 = 0; p2 <= pp.P.nfft; ++p2) ntab += pp.P.tab[p2] != nullptr;
             fprintf(stderr, "[plan] %s nfft=%d tables=%d gens=%d (", pp.col ? "col" : "row", pp.P.nfft, ntab, pp.P.ngen);
             for (int g2 = 0; g2 < pp.P.ngen; ++g2) fprintf(stderr, "%d@%d ", pp.P.gen[g2].kind, pp.P.gen[g2].pos);
-            fprintf(stderr, ") ctab=%d%d src=%d tiles=[%d,%d] in=[%d,%d]\n", pp.P.ctab_in != nullptr, pp.P.ctab_out != nullptr,
-                    pp.P.src != nullptr, pp.P.tile_lo, pp.P.tile_hi == 0x7fffffff ? -1 : pp.P.tile_hi, pp.P.in_lo, pp.P.in_hi);
+            fprintf(stderr, ") ctab=%d%d src=%d tiles=[%d,%d] in=[%d,%d] out=[%d,%d]\n", pp.P.ctab_in != nullptr, pp.P.ctab_out != nullptr,
+                    pp.P.src != nullptr, pp.P.tile_lo, pp.P.tile_hi == 0x7fffffff ? -1 : pp.P.tile_hi, pp.P.in_lo, pp.P.in_hi,
+                    pp.P.out_lo, pp.P.out_hi);
         }
     }
     if (readout && !plan.passes.empty()) {
