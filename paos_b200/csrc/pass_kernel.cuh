@@ -326,6 +326,10 @@ __device__ __forceinline__ void tma_store_tile(const CUtensorMap* tm, const void
                  : "memory");
 }
 
+// -x by its sign bit (bit-identical to x * -1, but not an instruction of the FP64 pipe)
+__device__ __forceinline__ double flip_sign(double x) { return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x)); }
+__device__ __forceinline__ float flip_sign(float x) { return __int_as_float(__float_as_int(x) ^ (int)0x80000000); }
+
 // ---- the pass kernel ---------------------------------------------------------------------------------
 // R: real type; N: line length; E: points per thread; W: lines per CTA; COL: lines are columns.
 // zero store of one tile (and of its read-out); out of line so that it does not share registers with the main path
@@ -565,12 +569,16 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
                 for (int j = 0; j < E; ++j) v[j] = v[j] * ldc_ro(tab + t + j * T);
             }
         } else {
-            // real scale, with the (-1)^index sign of an fftshift when flagged (index parity = t parity: T is even)
-            R s = (R)P.scl[pos];
-            if ((P.sgnmask >> pos & 1) && (t & 1)) s = -s;
+            // real scale (the planner moves it into a table of the pass whenever there is one), and the (-1)^index sign of an
+            // fftshift when flagged (index parity = t parity: T is even) as a flip of the sign bits on the integer pipe
+            const R s = (R)P.scl[pos];
             if (s != (R)1) {
 #pragma unroll
                 for (int j = 0; j < E; ++j) v[j] = v[j] * s;
+            }
+            if ((P.sgnmask >> pos & 1) && (t & 1)) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) v[j] = C<R>(flip_sign(v[j].x), flip_sign(v[j].y));
             }
         }
         if (pos == P.nfft) break;

@@ -562,6 +562,19 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
             }
             plan.edges.push_back(make_edge_spec(w, g, mem, axis));
         }
+        // A real scale commutes with everything a pass does (line transforms and diagonal factors are linear), so a position
+        // that carries nothing but a scale -- the 1/sqrt(N) of an orthonormal transform with no phase factor next to it --
+        // hands it to a position of the same pass that has a table anyway (tables carry their position's scale already) and
+        // saves E real multiplications per thread.  The product of the two scales is rounded once more: ~1e-16 relative.
+        static const bool fold_scales = getenv("PAOS_NO_SCALE_FOLD") == nullptr;
+        int host = -1;
+        for (int p = 0; p <= P.nfft && host < 0; ++p)
+            if (!acc[p].trivial()) host = p;
+        for (int p = 0; p <= P.nfft && fold_scales && host >= 0; ++p) {
+            if (!acc[p].trivial() || acc[p].scale == 1.0) continue;
+            acc[host].scale *= acc[p].scale;
+            acc[p].scale = 1.0;
+        }
         for (int p = 0; p <= P.nfft; ++p) {
             P.scl[p] = 1.0;
             P.tab[p] = nullptr;
@@ -616,7 +629,12 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
             for (int p2 = 0; p2 <= pp.P.nfft; ++p2) ntab += pp.P.tab[p2] != nullptr;
             fprintf(stderr, "[plan] %s nfft=%d tables=%d gens=%d (", pp.col ? "col" : "row", pp.P.nfft, ntab, pp.P.ngen);
             for (int g2 = 0; g2 < pp.P.ngen; ++g2) fprintf(stderr, "%d@%d ", pp.P.gen[g2].kind, pp.P.gen[g2].pos);
-            fprintf(stderr, ") ctab=%d%d src=%d tiles=[%d,%d] in=[%d,%d] out=[%d,%d]\n", pp.P.ctab_in != nullptr, pp.P.ctab_out != nullptr,
+            fprintf(stderr, ") pos[");
+            for (int p2 = 0; p2 <= pp.P.nfft; ++p2) {
+                if (pp.P.tab[p2]) fprintf(stderr, "T ");
+                else fprintf(stderr, "%s%g ", (pp.P.sgnmask >> p2 & 1) ? "s" : "", pp.P.scl[p2]);
+            }
+            fprintf(stderr, "] ctab=%d%d src=%d tiles=[%d,%d] in=[%d,%d] out=[%d,%d]\n", pp.P.ctab_in != nullptr, pp.P.ctab_out != nullptr,
                     pp.P.src != nullptr, pp.P.tile_lo, pp.P.tile_hi == 0x7fffffff ? -1 : pp.P.tile_hi, pp.P.in_lo, pp.P.in_hi,
                     pp.P.out_lo, pp.P.out_hi);
         }
