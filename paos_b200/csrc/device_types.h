@@ -72,7 +72,7 @@ struct PassParams {
     int tile_base;             // set by the launcher: tile of CTA 0 (blank tiles are not launched unless they have to store)
     int out_lo, out_hi;        // along-line index range the NEXT pass of the plan will read (its tile range: it runs along the
                                // other axis and touches nothing else); elements outside are not stored -- they stay stale
-    int pad;
+    int wide;                  // 1: this column pass runs on the wide-tile kernel (pass_dispatch.h) and its tiles count in that width
     const void* tmap_host;     // host pointer to the CUtensorMap of `dst` (column tiles of W complex x 256 rows), or null; the
                                // launcher copies it into BatchParams::tmap (a tensor map must sit in kernel parameter space)
     const void* tmap_real_host;  // same for `dst_real` (tiles of W reals x 256 rows) when a read-out is fused into the pass

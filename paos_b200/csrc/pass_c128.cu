@@ -4,10 +4,28 @@
 
 namespace paosb {
 
+// 2048^2 column passes come in two tile widths (pass_dispatch.h).  Default: ONE column per CTA, 128 threads, four CTAs per SM
+// like the row kernel -- the field moves through 16-byte-wide TMA boxes, a CTA that waits for its tile or drains its store
+// idles a quarter of the SM instead of half, and a barrier couples four warps instead of eight (measured, batches of 8:
+// column x4 261 -> 241 us, x6 314 -> 292, x8 351 -> 327).  Wide: TWO columns per CTA, two CTAs per SM, phase tables staged by
+// the bulk-copy engine -- the pass with the fused read-out, whose tile of reals must be 16 bytes per row for the TMA unit
+// (written straight from registers by single-column CTAs that pass takes 561 instead of 435 us).
+// -DPAOS_EXP_COLW_2048=2 builds the round's earlier layout (two columns everywhere) for the A/B measurement.
+#ifndef PAOS_EXP_COLW_2048
+#define PAOS_EXP_COLW_2048 1
+#endif
+#if PAOS_EXP_COLW_2048 == 1
+#define PAOS_COL_2048_NARROW launch_pass_t<double, 2048, 16, 1, true, 4>
+#else
+#define PAOS_COL_2048_NARROW launch_pass_t<double, 2048, 16, 2, true, 2>
+#endif
+#define PAOS_COL_2048_WIDE launch_pass_t<double, 2048, 16, 2, true, 2>
 #ifdef PAOS_EXP_ROW2  // experiment: two rows per CTA (256 threads, 2 CTAs/SM) like the column kernel
-#define PAOS_ROW_2048 PAOS_CASE(2048, 16, 2, 2, 2, 2)
+#define PAOS_ROW_2048 launch_pass_t<double, 2048, 16, 2, false, 2>
+#define PAOS_ROW_2048_W 2
 #else  // (five row CTAs per SM would need 96 registers: 1.7 KB of spills per thread, measured slower in round 1)
-#define PAOS_ROW_2048 PAOS_CASE(2048, 16, 1, 2, 4, 2)
+#define PAOS_ROW_2048 launch_pass_t<double, 2048, 16, 1, false, 4>
+#define PAOS_ROW_2048_W 1
 #endif
 // 512^2: five 128-thread CTAs per SM (96 registers; measured +3-4 % over four at 128 registers, six spill and lose 8 %)
 #ifndef PAOS_EXP_512_MINB
@@ -21,7 +39,6 @@ namespace paosb {
     PAOS_CASE(256, 16, 4, 4, 2, 2) \
     PAOS_ROW_512 \
     PAOS_CASE(1024, 16, 2, 4, 4, 2) \
-    PAOS_ROW_2048 \
     PAOS_CASE(4096, 16, 1, 2, 2, 1)
 
 #define PAOS_CASE(N, E, WR, WC, MR, MC)                                                              \
@@ -29,10 +46,13 @@ namespace paosb {
         return col ? launch_pass_t<double, N, E, WC, true, MC>(Ps, nb, tw1, tw2, st, device)                 \
                    : launch_pass_t<double, N, E, WR, false, MR>(Ps, nb, tw1, tw2, st, device);
 
-cudaError_t launch_pass_c128(int n, bool col, const PassParams* const* Ps, int nb, const void* tw1, const void* tw2,
+cudaError_t launch_pass_c128(int n, bool col, bool wide, const PassParams* const* Ps, int nb, const void* tw1, const void* tw2,
                              cudaStream_t st, int device) {
     switch (n) {
         PAOS_TILE_TABLE
+        case 2048:
+            if (!col) return PAOS_ROW_2048(Ps, nb, tw1, tw2, st, device);
+            return wide ? PAOS_COL_2048_WIDE(Ps, nb, tw1, tw2, st, device) : PAOS_COL_2048_NARROW(Ps, nb, tw1, tw2, st, device);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -41,9 +61,10 @@ cudaError_t launch_pass_c128(int n, bool col, const PassParams* const* Ps, int n
 #define PAOS_CASE(N, E, WR, WC, MR, MC) \
     case N:                             \
         return col ? WC : WR;
-int tile_width_c128(int n, bool col) {
+int tile_width_c128(int n, bool col, bool wide) {
     switch (n) {
         PAOS_TILE_TABLE
+        case 2048: return !col ? PAOS_ROW_2048_W : (wide ? 2 : PAOS_EXP_COLW_2048);
         default: return 1;
     }
 }

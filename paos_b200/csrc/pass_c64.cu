@@ -24,7 +24,7 @@ namespace paosb {
         return col ? launch_pass_t<float, N, E, WC, true, MC>(Ps, nb, tw1, tw2, st, device)                 \
                    : launch_pass_t<float, N, E, WR, false, MR>(Ps, nb, tw1, tw2, st, device);
 
-cudaError_t launch_pass_c64(int n, bool col, const PassParams* const* Ps, int nb, const void* tw1, const void* tw2,
+cudaError_t launch_pass_c64(int n, bool col, bool /*wide*/, const PassParams* const* Ps, int nb, const void* tw1, const void* tw2,
                              cudaStream_t st, int device) {
     switch (n) {
         PAOS_TILE_TABLE
@@ -36,7 +36,7 @@ cudaError_t launch_pass_c64(int n, bool col, const PassParams* const* Ps, int nb
 #define PAOS_CASE(N, E, WR, WC, MR, MC) \
     case N:                             \
         return col ? WC : WR;
-int tile_width_c64(int n, bool col) {
+int tile_width_c64(int n, bool col, bool /*wide*/) {
     switch (n) {
         PAOS_TILE_TABLE
         default: return 1;

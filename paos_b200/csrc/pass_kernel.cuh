@@ -294,11 +294,13 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
 // (measured on AIRS-CH0 2048^2, batches of 8: column passes 2-5 % faster, 521 -> 495 us for the dense final pass).  The row
 // kernel (one line per CTA, four CTAs per SM) would drop to three CTAs per SM and loses what it gains (profiles/README.md).
 // -DPAOS_TMA_TABLES=1 / =0 forces it on / off everywhere for the A/B measurement.
-template <int N, bool COL> __host__ __device__ constexpr bool use_tma_tables() {
+// A single-column CTA (W = 1: the 2048^2 column passes without a read-out, four CTAs per SM like the row kernel) has no room
+// for the staging buffer either.
+template <int N, bool COL, int W> __host__ __device__ constexpr bool use_tma_tables() {
 #ifdef PAOS_TMA_TABLES
     return PAOS_TMA_TABLES != 0;
 #else
-    return COL && N >= 2048;
+    return COL && N >= 2048 && W >= 2;
 #endif
 }
 
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
     const int line = tile * W + w;
     C<R>* sm = smem + w * G::line_stride(COL ? W : 1, (int)sizeof(C<R>));
     auto sync = [] { __syncthreads(); };
-    constexpr bool kTmaTables = use_tma_tables<N, COL>();
+    constexpr bool kTmaTables = use_tma_tables<N, COL, W>();
     // TMA variant: [exchange buffers of the W lines][one table of N entries][mbarrier]
     C<R>* tabbuf = smem + W * G::line_stride(COL ? W : 1, (int)sizeof(C<R>));
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(kTmaTables ? tabbuf + N : tabbuf);
@@ -703,7 +705,7 @@ cudaError_t launch_pass_cap(const PassParams* const* Ps, int nb, const void* tw1
     using G = LineGeom<N, E>;
     constexpr int threads = W * G::T;
     const size_t smem = (size_t)W * G::line_stride(COL ? W : 1, (int)sizeof(C<R>)) * sizeof(C<R>) +
-                        (use_tma_tables<N, COL>() ? (size_t)N * sizeof(C<R>) + 16 : (use_tma_field<N, COL>() ? 16 : 0));
+                        (use_tma_tables<N, COL, W>() ? (size_t)N * sizeof(C<R>) + 16 : (use_tma_field<N, COL>() ? 16 : 0));
     auto kern = pass_kernel<R, N, E, W, COL, MINB, CAP>;
     static bool configured[64] = {};  // per instantiation and device
     if (!configured[device & 63]) {

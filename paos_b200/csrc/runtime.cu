@@ -216,7 +216,7 @@ struct paos_wfo {
     bool recording = false;
     std::vector<Rec> program;
     std::vector<void*> retired_pools;  // table pools outgrown while recording: still referenced by the program
-    std::map<const void*, CUtensorMap*> tmaps;  // tensor maps of the field buffers (column tiles), built on first use
+    std::map<std::pair<const void*, int>, CUtensorMap*> tmaps;  // tensor maps of the field buffers (column tiles), built on first use
 
     paos_stats stats{};
     bool timing = false;
@@ -236,10 +236,11 @@ static int set_device(paos_wfo* w) {
 // Tensor map of an n x n complex field for the column passes' TMA tile stores: a 2-D tensor of reals (2n per row), boxes of
 // 2W reals x 256 rows.  cuTensorMapEncodeTiled is fetched from the driver at run time (no link against libcuda); null when
 // the variant is not compiled in or the driver refuses.
-static const CUtensorMap* field_tmap(paos_wfo* w, const void* field, bool real_readout = false) {
+static const CUtensorMap* field_tmap(paos_wfo* w, const void* field, bool real_readout = false, bool wide = false) {
 #if PAOS_TMA_FIELD
     if (w->n < PAOS_TMA_FIELD_MIN_N || !field) return nullptr;
-    auto it = w->tmaps.find(field);
+    const std::pair<const void*, int> key(field, (real_readout ? 1 : 0) | (wide ? 2 : 0));
+    auto it = w->tmaps.find(key);
     if (it != w->tmaps.end()) return it->second;
     if (w->tmaps.size() > 4096) {  // read-out destinations come and go: keep the cache bounded
         for (auto& kv : w->tmaps) delete kv.second;
@@ -256,7 +257,7 @@ static const CUtensorMap* field_tmap(paos_wfo* w, const void* field, bool real_r
     }();
     CUtensorMap* tm = nullptr;
     if (encode) {
-        const int W = tile_width(w->n, w->dtype, true);
+        const int W = tile_width(w->n, w->dtype, true, wide);
         const bool c128 = w->dtype == PAOS_C128;
         const int per = real_readout ? 1 : 2;  // reals per pixel: a read-out (|.|, angle, |.|^2) or the complex field
         const cuuint64_t gdim[2] = {(cuuint64_t)per * w->n, (cuuint64_t)w->n};
@@ -264,7 +265,8 @@ static const CUtensorMap* field_tmap(paos_wfo* w, const void* field, bool real_r
         const cuuint32_t box[2] = {(cuuint32_t)(per * W), 256u};
         const cuuint32_t estr[2] = {1u, 1u};
         tm = new CUtensorMap;
-        CUresult r = encode(tm, c128 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(field), gdim, gstride, box,
+        const size_t row_bytes = (size_t)per * W * (w->elem / 2);  // the TMA unit moves rows of 16 bytes or more
+        CUresult r = row_bytes < 16 ? CUDA_ERROR_INVALID_VALUE : encode(tm, c128 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(field), gdim, gstride, box,
                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -272,7 +274,7 @@ static const CUtensorMap* field_tmap(paos_wfo* w, const void* field, bool real_r
             tm = nullptr;
         }
     }
-    w->tmaps[field] = tm;  // null is remembered too: the direct stores are used
+    w->tmaps[key] = tm;  // null is remembered too: the direct stores are used
     return tm;
 #else
     (void)w;
@@ -606,6 +608,30 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
         pp.P = P;
         plan.passes.push_back(pp);
     }
+    if (readout && !plan.passes.empty()) {
+        PlannedPass& last = plan.passes.back();
+        last.P.readout = readout;
+        last.P.dst_real = dst_real;
+        if (last.col && has_wide_tiles(w->n, w->dtype)) {
+            // a column pass with a fused read-out runs on the wide-tile kernel (pass_dispatch.h): recount its tiles, and the
+            // band it leaves, in that width (a superset of the lines: the extra ones are transformed and come out as zeros)
+            const int n = w->n, Wn = tile_width(n, w->dtype, true, false), Ww = tile_width(n, w->dtype, true, true);
+            PassParams& P = last.P;
+            P.wide = 1;
+            if (P.tile_lo > 0 || P.tile_hi != 0x7fffffff) {
+                const long long line_lo = (long long)std::max(0, P.tile_lo) * Wn;
+                const long long line_hi = P.tile_hi < 0 ? -1 : std::min<long long>(n - 1, (long long)P.tile_hi * Wn + Wn - 1);
+                P.tile_lo = (int)(line_lo / Ww);
+                P.tile_hi = line_hi >= line_lo ? (int)(line_hi / Ww) : -1;
+                if (band.valid) {
+                    band.lo = P.tile_lo * Ww;
+                    band.hi = P.tile_hi < 0 ? -1 : std::min(n - 1, P.tile_hi * Ww + Ww - 1);
+                }
+            }
+            P.tmap_host = field_tmap(w, field, false, true);
+        }
+        if (last.col) last.P.tmap_real_host = field_tmap(w, dst_real, true, last.P.wide != 0);
+    }
     // Look ahead: a pass followed, inside this plan, by a pass along the other axis is read by that pass only, and that
     // pass touches nothing outside its tile range (its blank tiles are neither loaded nor stored).  Along the lines of the
     // first pass that range is a stretch of indices: only that stretch is stored (a zoom-4 beam: a quarter to 40 % of
@@ -616,7 +642,7 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
         const PlannedPass& b = plan.passes[i + 1];
         if (a.col == b.col || !a.P.dst || b.P.src != a.P.dst || b.P.zero_fill) continue;
         if (b.P.tile_lo <= 0 && b.P.tile_hi == 0x7fffffff) continue;
-        const int n = w->n, Wb = tile_width(n, w->dtype, b.col);
+        const int n = w->n, Wb = tile_width(n, w->dtype, b.col, b.P.wide != 0);
         const int lo = std::max(0, b.P.tile_lo) * Wb;
         const int hi = b.P.tile_hi < 0 ? -1 : (int)std::min<long long>(n - 1, (long long)b.P.tile_hi * Wb + Wb - 1);
         a.P.out_lo = hi >= lo ? lo : n;  // empty: [n, n] matches no index
@@ -639,18 +665,13 @@ static int build_plan(paos_wfo* w, const std::vector<Op>& ops, Plan& plan, int r
                     pp.P.out_lo, pp.P.out_hi);
         }
     }
-    if (readout && !plan.passes.empty()) {
-        plan.passes.back().P.readout = readout;
-        plan.passes.back().P.dst_real = dst_real;
-        if (plan.passes.back().col) plan.passes.back().P.tmap_real_host = field_tmap(w, dst_real, true);
-    }
     return PAOS_OK;
 }
 
 static void account_pass(paos_wfo* w, bool col, const PassParams& P) {
     w->stats.passes_planned++;
     w->stats.line_ffts_run += (uint64_t)P.nfft;
-    const int W = tile_width(w->n, w->dtype, col), tiles = w->n / W;
+    const int W = tile_width(w->n, w->dtype, col, P.wide != 0), tiles = w->n / W;
     const int active = std::max(0, std::min(P.tile_hi, tiles - 1) - std::max(P.tile_lo, 0) + 1);
     w->stats.lines_transformed += (uint64_t)P.nfft * (uint64_t)active * (uint64_t)W;
     int tabs = (P.ctab_in ? 1 : 0) + (P.ctab_out ? 1 : 0);
@@ -674,8 +695,9 @@ static int launch_pass_group(paos_wfo* lead, bool col, const PassParams* const* 
         }
         CU(cudaEventRecord(ea, st));
     }
-    cudaError_t e = (lead->dtype == PAOS_C128) ? launch_pass_c128(lead->n, col, Ps, nb, lead->tw.tw1, lead->tw.tw2, st, lead->device)
-                                               : launch_pass_c64(lead->n, col, Ps, nb, lead->tw.tw1, lead->tw.tw2, st, lead->device);
+    const bool wide = Ps[0]->wide != 0;  // the caller groups passes of one width
+    cudaError_t e = (lead->dtype == PAOS_C128) ? launch_pass_c128(lead->n, col, wide, Ps, nb, lead->tw.tw1, lead->tw.tw2, st, lead->device)
+                                               : launch_pass_c64(lead->n, col, wide, Ps, nb, lead->tw.tw1, lead->tw.tw2, st, lead->device);
     if (e != cudaSuccess) return fail(PAOS_ERR_CUDA, "pass kernel launch failed: %s", cudaGetErrorString(e));
     if (lead->timing) {
         CU(cudaEventRecord(eb, st));
@@ -822,10 +844,14 @@ static int execute_programs(paos_wfo** ws, int nb) {
             if ((rc = launch_norm2_group(lead, norms.data(), (int)norms.size(), st))) return rc;
         } else {
             const bool col = n_col > n_row;
-            int k = 0;
+            int k = 0, wide = -1;  // one launch = one kernel: same axis and same tile width (the first head decides)
             for (int b = 0; b < nb; ++b)
-                if (at[b] < ws[b]->program.size() && ws[b]->program[at[b]].kind == REC_PASS && ws[b]->program[at[b]].col == col)
+                if (at[b] < ws[b]->program.size() && ws[b]->program[at[b]].kind == REC_PASS && ws[b]->program[at[b]].col == col) {
+                    const int wd = ws[b]->program[at[b]].P.wide;
+                    if (wide < 0) wide = wd;
+                    if (wd != wide) continue;
                     group[k++] = &ws[b]->program[at[b]++].P;
+                }
             if ((rc = launch_pass_group(lead, col, group, k, st))) return rc;
         }
     }
