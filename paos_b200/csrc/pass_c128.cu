@@ -20,6 +20,16 @@ namespace paosb {
 #define PAOS_COL_2048_NARROW launch_pass_t<double, 2048, 16, 2, true, 2>
 #endif
 #define PAOS_COL_2048_WIDE launch_pass_t<double, 2048, 16, 2, true, 2>
+// 4096^2: the same two widths (256 or 512 threads per CTA, two CTAs or one per SM; AIRS-CH0 4096^2: 417 -> 443 PSF/s)
+#ifndef PAOS_EXP_COLW_4096
+#define PAOS_EXP_COLW_4096 1
+#endif
+#if PAOS_EXP_COLW_4096 == 1
+#define PAOS_COL_4096_NARROW launch_pass_t<double, 4096, 16, 1, true, 2>
+#else
+#define PAOS_COL_4096_NARROW launch_pass_t<double, 4096, 16, 2, true, 1>
+#endif
+#define PAOS_COL_4096_WIDE launch_pass_t<double, 4096, 16, 2, true, 1>
 #ifdef PAOS_EXP_ROW2  // experiment: two rows per CTA (256 threads, 2 CTAs/SM) like the column kernel
 #define PAOS_ROW_2048 launch_pass_t<double, 2048, 16, 2, false, 2>
 #define PAOS_ROW_2048_W 2
@@ -38,8 +48,7 @@ namespace paosb {
     PAOS_CASE(128, 8, 8, 8, 1, 1) \
     PAOS_CASE(256, 16, 4, 4, 2, 2) \
     PAOS_ROW_512 \
-    PAOS_CASE(1024, 16, 2, 4, 4, 2) \
-    PAOS_CASE(4096, 16, 1, 2, 2, 1)
+    PAOS_CASE(1024, 16, 2, 4, 4, 2)
 
 #define PAOS_CASE(N, E, WR, WC, MR, MC)                                                              \
     case N:                                                                                          \
@@ -53,6 +62,9 @@ cudaError_t launch_pass_c128(int n, bool col, bool wide, const PassParams* const
         case 2048:
             if (!col) return PAOS_ROW_2048(Ps, nb, tw1, tw2, st, device);
             return wide ? PAOS_COL_2048_WIDE(Ps, nb, tw1, tw2, st, device) : PAOS_COL_2048_NARROW(Ps, nb, tw1, tw2, st, device);
+        case 4096:
+            if (!col) return launch_pass_t<double, 4096, 16, 1, false, 2>(Ps, nb, tw1, tw2, st, device);
+            return wide ? PAOS_COL_4096_WIDE(Ps, nb, tw1, tw2, st, device) : PAOS_COL_4096_NARROW(Ps, nb, tw1, tw2, st, device);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -65,6 +77,7 @@ int tile_width_c128(int n, bool col, bool wide) {
     switch (n) {
         PAOS_TILE_TABLE
         case 2048: return !col ? PAOS_ROW_2048_W : (wide ? 2 : PAOS_EXP_COLW_2048);
+        case 4096: return !col ? 1 : (wide ? 2 : PAOS_EXP_COLW_4096);
         default: return 1;
     }
 }
