@@ -41,6 +41,8 @@ namespace paosb {
 #ifndef PAOS_EXP_512_MINB
 #define PAOS_EXP_512_MINB 5
 #endif
+// (1024^2 column kernel at two columns per CTA and four CTAs per SM, with or without TMA tiles: within +-3 % of four columns
+// and two CTAs on AIRS / TA-Ground, -7 % on Hubble; TMA tiles at 512^2 and 1024^2: -1..-4 % -- profiles/README.md)
 #define PAOS_ROW_512 PAOS_CASE(512, 8, 2, 2, PAOS_EXP_512_MINB, PAOS_EXP_512_MINB)
 //                 N    E  Wrow Wcol minb(row) minb(col)
 #define PAOS_TILE_TABLE \

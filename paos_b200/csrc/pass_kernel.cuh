@@ -316,6 +316,12 @@ template <int N, bool COL> __host__ __device__ constexpr bool use_tma_field() {
     return COL && PAOS_TMA_FIELD != 0 && N >= PAOS_TMA_FIELD_MIN_N;
 }
 constexpr int TMA_BOX_ROWS = 256;
+#ifndef PAOS_TMA_FIELD_LOAD  // A/B switches: tile loads / tile stores of the complex field through the TMA unit
+#define PAOS_TMA_FIELD_LOAD 1
+#endif
+#ifndef PAOS_TMA_FIELD_STORE
+#define PAOS_TMA_FIELD_STORE 1
+#endif
 __device__ __forceinline__ void tma_load_tile(void* smem_dst, const CUtensorMap* tm, int c0, int c1, void* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                      smem_u32(smem_dst)),
@@ -416,7 +422,7 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
     C<R> v[E];
     bool loaded = false;
     if constexpr (kTmaField) {
-        if (src && (BP.use_tmap & 1)) {
+        if (src && (BP.use_tmap & 1) && PAOS_TMA_FIELD_LOAD) {
             // the live rows [in_lo, in_hi] of this CTA's W columns arrive as TMA boxes of W x 256 rows in the exchange buffer
             // (idle until the first transform); the threads then pick their elements with conflict-free shared loads
             const int base = P.in_lo, rows = P.in_hi < N ? P.in_hi - base + 1 : 0;  // empty band: in_lo = in_hi = N
@@ -633,7 +639,7 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
     // let the next kernel of the stream get its CTAs scheduled while this grid stores (it waits for our completion above)
     asm volatile("griddepcontrol.launch_dependents;");
     if constexpr (use_tma_field<N, COL>()) {
-        if (dst && (BP.use_tmap & 1) && !P.readout) {
+        if (dst && (BP.use_tmap & 1) && !P.readout && PAOS_TMA_FIELD_STORE) {
             // tile [row][W] in the exchange buffer, then W x 256-row boxes to the TMA unit
             // only the boxes that hold rows [out_lo, out_hi] leave: the next pass reads nothing else (device_types.h)
             const int box_lo = P.out_lo / TMA_BOX_ROWS, box_hi = P.out_hi < N ? P.out_hi / TMA_BOX_ROWS : -1;
