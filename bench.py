@@ -87,6 +87,7 @@ def _cpu_worker(args):
     """One chain of the sweep on one core.  Returns (seconds, path of the saved IMAGE_PLANE amplitude or None)."""
     grid, n_wl, index, ut, keep_dir = args
     os.environ["OMP_NUM_THREADS"] = "1"
+    _restore_affinity()
     import numpy as np
 
     from oracle import refload
@@ -133,11 +134,26 @@ def _cpu_worker(args):
     return dt, out
 
 
-def cpu_cores():
+def _full_affinity():
+    """The CPUs this run may use: the affinity the bench was started with (the GPU arm narrows its own to one NUMA node)."""
+    spec = os.environ.get("PAOS_BENCH_AFFINITY")
+    if spec:
+        return {int(c) for c in spec.split(",") if c}
     try:
-        return len(os.sched_getaffinity(0))
+        return set(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        return set(range(os.cpu_count() or 1))
+
+
+def _restore_affinity():
+    try:
+        os.sched_setaffinity(0, _full_affinity())
+    except (AttributeError, OSError):
+        pass
+
+
+def cpu_cores():
+    return len(_full_affinity()) or 1
 
 
 def cpu_chains(pool, indices, grid=GRID, n_wl=N_WL, ut=0.0, keep_dir=None):
@@ -351,7 +367,10 @@ def run_ours(args):
     jobs = jobs_all[lo:hi]
     counts = [b - a for a, b in blocks]
 
-    numa = sweep_mod.bind_to_gpu_numa(local_rank) if world > 1 else None
+    # pin this process (and the pinned host buffers it allocates next) to the NUMA node of its GPU; the CPU workers of the
+    # baseline leg go back to the full affinity recorded here (PAOS_BENCH_AFFINITY, applied in _cpu_worker)
+    os.environ.setdefault("PAOS_BENCH_AFFINITY", ",".join(str(c) for c in sorted(os.sched_getaffinity(0))))
+    numa = sweep_mod.bind_to_gpu_numa(local_rank) if (world > 1 or not os.environ.get("PAOS_BENCH_NO_NUMA")) else None
     sw = sweep_mod.Sweep(grid, device=local_rank, dtype=args.dtype, slots=args.slots, what="psf", batch=args.batch)
     args.slots, args.batch = len(sw.streams), sw.batch
     # multi-GPU: the local stack of the destination rank is a view into the gathered [world * n, N, N] stack
@@ -647,7 +666,7 @@ def run_ours(args):
                     "note": "paos_b200.sweep.Sweep.run over host job dicts; inputs are lens-prescription scalars (kernel "
                             "arguments, no array uploads); every PSF (N*N fp64) is copied to pinned host memory inside the timed region"},
             "gpu_launches": launches * world,
-            "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "numa_node": numa,
             "wall_ms_per_psf": 1e3 * t_host / (len(jobs) * args.steps),
             "host_plan_ms_per_psf": 1e-3 * (st1["host_plan_us"] - st0["host_plan_us"]) / (len(jobs) * args.steps),
             "fft2_per_step": int(st1["fft2_recorded"] - st0["fft2_recorded"]) // args.steps * world,

@@ -203,3 +203,24 @@ def test_ta_ground_psd_every_field_against_oracle():
     out = out.cpu().numpy()
     for k, ref in enumerate(refs):
         assert relerr(out[k], ref) <= TOL["complex128"], jobs[k]["tag"]
+
+
+def test_rectangular_apertures_between_propagations_2048():
+    """Decentred rectangular apertures at 2048^2 between lenses and propagations: their separable sub-pixel counts travel
+    in the phase tables of the pass (TERM_COUNT), which makes those tables the only ones that are not symmetric about
+    N/2 -- the case the single-column / row kernels of the large grids must tell apart when they stage tables by halves."""
+    from helpers import Pair
+
+    n = 2048
+    p = Pair(1.0, 1.5e-6, n, 4)
+    p.call("aperture", 0.0, 0.0, hx=0.5, hy=0.5, shape="elliptical")
+    p.call("make_stop")
+    p.call("lens", 40.0)
+    p.call("aperture", 0.0313, -0.0171, hx=0.41, hy=0.33, shape="rectangular")
+    p.call("propagate", 3.0)
+    p.call("aperture", -0.052, 0.0207, hx=0.0213, hy=0.6, shape="rectangular", obscuration=True)
+    p.call("lens", -25.0)
+    p.call("propagate", 2.0)
+    p.call("aperture", 0.01, 0.0, hx=0.3, hy=0.35, shape="rectangular")
+    p.call("propagate", 1.5)
+    p.check()
