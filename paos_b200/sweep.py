@@ -10,6 +10,8 @@ Jobs (see ``paos_b200/configs.py``) are independent, so the only parallel struct
   rank, no communication during propagation, and ONE gather of the result stack at the end
   (:func:`gather_stack`, NCCL over NVLink on GPUs, gloo in the CPU tests).
 """
+import os
+
 import numpy as np
 
 from . import _lib
@@ -106,7 +108,18 @@ class Sweep:
         self.torch = torch
         self.tdev = torch.device("cuda", self.device)
         self.rdtype = torch.float64 if dtype == "complex128" else torch.float32
-        self.streams = [torch.cuda.Stream(device=self.tdev) for _ in range(slots)]
+        # PAOS_SWEEP_PRIORITIES=1 (off by default): slot s gets a higher stream priority than slot s + 1, so that the slots'
+        # batches finish one after the other instead of all at once and the device-to-host copies of an end-to-end sweep
+        # start after one batch time instead of `slots` of them.  Measured on one box (profiles/README.md): with
+        # PAOS_SWEEP_FIRST_GROUP=2 as well the end-to-end sweep gains 6.5 % (1 415 -> 1 508 PSF/s), the device-resident one
+        # loses 1.6 % (2 120 -> 2 087): the default stays with the device-resident rate.
+
+        least, greatest = torch.cuda.Stream.priority_range()  # e.g. (0, -5): smaller is more urgent
+        levels = abs(greatest - least)
+        use_prio = os.environ.get("PAOS_SWEEP_PRIORITIES", "0") == "1" and slots > 1 and levels > 0
+        step = -1 if greatest < least else 1
+        self.streams = [torch.cuda.Stream(device=self.tdev, priority=(least + step * min(levels, slots - 1 - s)) if use_prio else least)
+                        for s in range(slots)]
         # device-to-host copies of finished results run on a stream of their own, so that a slot's next batch of kernels
         # does not queue behind 8 x 32 MiB of PCIe traffic
         self.copy_streams = [torch.cuda.Stream(device=self.tdev) for _ in range(slots)]
@@ -288,7 +301,15 @@ class Sweep:
                 ev.record(stream)
                 on_group(ks[0], ks[-1] + 1, ev)
 
-        groups = [list(range(g, min(g + B, len(jobs)))) for g in range(0, len(jobs), B)]
+        # the first group of every slot may be smaller (PAOS_SWEEP_FIRST_GROUP, experiment): results start to flow earlier
+        first = int(os.environ.get("PAOS_SWEEP_FIRST_GROUP", "0") or 0)
+        if out.shape[0] < len(jobs) or (host_out is not None and host_out.shape[0] < len(jobs)):
+            first = 0  # rings rely on every slot owning the same rows group after group: equal groups only
+        groups, g = [], 0
+        while g < len(jobs):
+            size = first if (0 < first < B and len(groups) < nslots) else B
+            groups.append(list(range(g, min(g + size, len(jobs)))))
+            g += size
 
         def do_slot(s):
             # one host thread per slot: the C++ planner and the launches run without the GIL (ctypes releases it),
