@@ -187,6 +187,8 @@ template <int N_, int E_> struct LineGeom {
 // with t = q E + n3.  Rows are TP = T + 1 (odd) elements long, so the eight lanes of a 16-byte shared-memory phase
 // (consecutive t, hence consecutive n3 or consecutive columns) hit eight different bank groups in all six patterns.
 // Two barriers per transform instead of four; the arithmetic and its order are unchanged (results are bit-identical).
+// tests/test_fft_layouts.py restates the six address maps in numpy and checks the transform, the in-place property and the
+// bank groups for every three-stage size.
 // MID is called by every thread right after the first barrier (the column kernels start the bulk copy of the next
 // phase table there: every thread has consumed the current one before its stage-1 butterfly).
 #ifndef PAOS_INPLACE_EXCHANGE
