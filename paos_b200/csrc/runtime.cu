@@ -217,6 +217,7 @@ struct paos_wfo {
     std::vector<Rec> program;
     std::vector<void*> retired_pools;  // table pools outgrown while recording: still referenced by the program
     std::map<std::pair<const void*, int>, CUtensorMap*> tmaps;  // tensor maps of the field buffers (column tiles), built on first use
+    std::vector<CUtensorMap*> retired_tmaps;                    // dropped from the cache while recorded passes may still use them
 
     paos_stats stats{};
     bool timing = false;
@@ -243,7 +244,10 @@ static const CUtensorMap* field_tmap(paos_wfo* w, const void* field, bool real_r
     auto it = w->tmaps.find(key);
     if (it != w->tmaps.end()) return it->second;
     if (w->tmaps.size() > 4096) {  // read-out destinations come and go: keep the cache bounded
-        for (auto& kv : w->tmaps) delete kv.second;
+        // passes that are planned or recorded but not yet launched still point at these maps: retire them, free them at the
+        // next paos_wfo_sync / destroy (128 bytes each)
+        for (auto& kv : w->tmaps)
+            if (kv.second) w->retired_tmaps.push_back(kv.second);
         w->tmaps.clear();
     }
     typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -1066,6 +1070,7 @@ int paos_wfo_destroy(paos_wfo* w) {
     if (w->tab_pool) cudaFree(w->tab_pool);
     for (void* p : w->retired_pools) cudaFree(p);
     for (auto& kv : w->tmaps) delete kv.second;
+    for (CUtensorMap* tm : w->retired_tmaps) delete tm;
     if (w->partials) cudaFree(w->partials);
     if (w->slots) cudaFree(w->slots);
     if (w->own_field && w->field) cudaFree(w->field);
@@ -1108,6 +1113,8 @@ int paos_wfo_sync(paos_wfo* w) {
     CU(cudaStreamSynchronize(w->stream));
     for (void* p : w->retired_pools) cudaFree(p);
     w->retired_pools.clear();
+    for (CUtensorMap* tm : w->retired_tmaps) delete tm;
+    w->retired_tmaps.clear();
     return resolve_timing(w);
 }
 
