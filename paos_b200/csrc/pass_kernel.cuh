@@ -215,8 +215,6 @@ static __device__ __noinline__ double gen_factor_tilt(const GenOp& g, int ix, in
 // single-op version used by the stop reduction (aux_kernels.cu)
 template <typename R>
 __device__ __forceinline__ void apply_gen(C<R>& v, const GenOp& g, int ix, int iy, int n) {
-    PassParams* none = nullptr;
-    (void)none;
     double re = 1.0, im = 0.0;
     switch (g.kind) {
         case GEN_ELLIPSE: {
@@ -697,7 +695,6 @@ __global__ void __launch_bounds__(W*(N / E), MINB)
         for (int j = 0; j < E; ++j) {
             const int idx = t + j * T;
             const size_t ga = COL ? ((size_t)idx * N + line) : ((size_t)line * N + idx);
-            // |.|^2 inline (the common sweep read-out); |.| and angle go through the out-of-line libm path
             // |.|^2 inline (the common sweep read-out); |.| and angle go through the out-of-line libm path
             out[ga] = (P.readout == 3) ? v[j].x * v[j].x + v[j].y * v[j].y : readout_value<R>(v[j], P.readout);
         }
