@@ -310,3 +310,21 @@ def test_wfe_column_ranges():
     assert parse_wfe_columns("a.csv,3-6") == ("a.csv", [3, 4, 5, 6])
     assert parse_wfe_columns("dir/a.csv,0:10:4") == ("dir/a.csv", [0, 4, 8])
     assert parse_wfe_columns("a.csv,2.0") == ("a.csv", [2])
+
+
+def test_bench_cpu_arm_keeps_the_full_affinity(monkeypatch):
+    """bench.py narrows the GPU arm's process to the NUMA node of its GPU; the CPU workers of the baseline leg must count
+    and use the CPUs the bench was started with (PAOS_BENCH_AFFINITY), not the narrowed set."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import importlib
+
+    bench = importlib.import_module("bench")
+    allowed = sorted(os.sched_getaffinity(0))
+    monkeypatch.delenv("PAOS_BENCH_AFFINITY", raising=False)
+    assert bench._full_affinity() == set(allowed) and bench.cpu_cores() == len(allowed)
+    monkeypatch.setenv("PAOS_BENCH_AFFINITY", ",".join(str(c) for c in allowed[:1]))
+    assert bench._full_affinity() == {allowed[0]} and bench.cpu_cores() == 1
+    monkeypatch.setenv("PAOS_BENCH_AFFINITY", ",".join(str(c) for c in allowed))
+    bench._restore_affinity()  # a no-op here; must not raise
+    assert set(os.sched_getaffinity(0)) == set(allowed)
